@@ -1,0 +1,174 @@
+/* b200scn -- C-ABI of the B200-native sparse U-ResNet hot path (libb200scn.so).
+ *
+ * This is the drop-in boundary: the set of entry points a replacement for SparseConvNet's
+ * native extension (`sparseconvnet.SCN`, reached from
+ * /root/reference/uresnet/models/uresnet_sparse.py:9,19-24 through `import sparseconvnet as scn`)
+ * has to provide for the modules that model uses.  Each group below names the scn module /
+ * reference call site it serves.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer in the caller's current CUDA
+ *     context unless its name ends in `_host`; the last argument is a cudaStream_t passed as
+ *     void*.  The library never allocates or frees caller memory and never synchronises.
+ *   - return value: 0 = ok, <0 = error (message via b200scn_last_error(), thread-local).
+ *   - row counts come in two forms: `n_cap` (host int, sizes the grid and bounds every
+ *     access) and `n_dev` (device int32*, may be NULL).  If n_dev != NULL the kernels use
+ *     min(*n_dev, n_cap) as the live row count.  That is what lets a whole training step be
+ *     captured in one CUDA graph although the number of active sites changes per event.
+ *   - feature matrices are row-major fp32 with an explicit row stride (`ld*`, in elements),
+ *     so a layer can read or write a column slice of a wider matrix (skip-concat buffers).
+ *   - index tables are int32, offset-major: table[k * ld + row], -1 = no entry.
+ *   - weights: W[k][ci][co] addressed as W[k*w_sk + ci*w_si + co*w_so]; `kflip` != 0 makes
+ *     the kernel use W[K-1-k] for table offset k (dgrad of a submanifold conv).
+ *   - site keys: 64-bit, sample << 48 | c0 << 32 | c1 << 16 | c2 (3D) or sample << 48 | c0 << 16 | c1
+ *     (2D); coordinates and sample ids must be in [0, 65535).
+ */
+#ifndef B200SCN_H
+#define B200SCN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SCN_OK 0
+#define B200SCN_ERR_ARG (-1)
+#define B200SCN_ERR_CUDA (-2)
+#define B200SCN_ERR_UNSUPPORTED (-3)
+
+/* coordinate dtypes accepted by b200scn_input_build */
+#define B200SCN_I32 0
+#define B200SCN_I64 1
+#define B200SCN_F32 2
+#define B200SCN_F64 3
+
+/* math modes of the gather-GEMM kernels */
+#define B200SCN_MATH_FP32 0   /* FFMA, exact fp32 products                                  */
+#define B200SCN_MATH_TF32X3 1 /* mma.sync tf32, 3-term split: fp32-equivalent accuracy       */
+#define B200SCN_MATH_TF32 2   /* mma.sync tf32, single pass: ~1e-3 relative                  */
+
+const char* b200scn_last_error(void);
+int b200scn_version(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int b200scn_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * (i) metadata / rulebook  -- replaces scn's CPU Metadata: InputLayer rules
+ * (uresnet_sparse.py:20), SubmanifoldConvolution rules (:21), Convolution/Deconvolution
+ * rules inside scn.UNet (:22).
+ * ------------------------------------------------------------------------------------- */
+
+/* hash slots (power of two, >= 2 * n_cap) the caller must allocate: keys uint64[slots], vals int32[slots] */
+int64_t b200scn_hash_slots(int64_t n_cap);
+/* bytes of scratch the rulebook calls need for n_cap rows */
+int64_t b200scn_rulebook_scratch_bytes(int64_t n_cap);
+
+/* InputLayer(mode=3) rules.  coords [n_cap, D+1] (or [n_cap, D] when has_sample_col == 0) of
+ * dtype coord_dtype, row stride ld_coords elements.
+ * Outputs: in2row[n_cap]            row of every input point (first-occurrence order)
+ *          ukeys[n_cap]             key of every active row
+ *          n_act_dev[1]             number of active rows
+ *          first_idx[n_cap]         input index of each active row's first occurrence
+ *          seg_off[n_cap + 1], seg[n_cap]  CSR of the *additional* (duplicate) inputs of each
+ *                                   row, ascending input index (for in-order mode-3 sums)
+ *          err_dev[1]               set non-zero when a coordinate is out of key range
+ * The hash table (tkeys, tvals) is left mapping key -> row for later probes. */
+int b200scn_input_build(const void* coords, int coord_dtype, int64_t ld_coords, int has_sample_col, int D,
+                        int64_t n_cap, const int32_t* n_dev, uint64_t* tkeys, int32_t* tvals, int64_t slots,
+                        int32_t* in2row, uint64_t* ukeys, int32_t* n_act_dev, int32_t* first_idx,
+                        int32_t* seg_off, int32_t* seg, int32_t* err_dev, void* scratch, int64_t scratch_bytes,
+                        void* stream);
+
+/* Convolution(filter == stride == s) rules: next level's active set in discovery order.
+ * Outputs: parent[n_cap], kofs[n_cap] (offset code of each fine row inside its parent),
+ *          ukeys_next[n_cap], n_next_dev[1], child[K * ld_child] (K = s^D; row of the child
+ *          at offset k of each coarse row, -1 = none).  (tkeys, tvals) = table of the new level. */
+int b200scn_level_down(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_dev, int D, int s, uint64_t* tkeys,
+                       int32_t* tvals, int64_t slots, int32_t* parent, uint8_t* kofs, uint64_t* ukeys_next,
+                       int32_t* n_next_dev, int32_t* child, int64_t ld_child, void* scratch,
+                       int64_t scratch_bytes, void* stream);
+
+/* SubmanifoldConvolution(filter k, odd) rules as a neighbour table nbr[K * ld], K = k^D,
+ * offset index enumerating the box with the last dimension fastest. */
+int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_dev, int D, int k,
+                       const uint64_t* tkeys, const int32_t* tvals, int64_t slots, int32_t* nbr, int64_t ld,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (ii) gather-GEMM(-scatter) convolutions -- SubmanifoldConvolution / Convolution /
+ * Deconvolution / NetworkInNetwork forward, dgrad, wgrad.
+ * ------------------------------------------------------------------------------------- */
+
+/* out[o, :] (+)= sum_k in[table[k][o], :] @ W[k]     (table == NULL: K must be 1, identity)
+ * serves: subm fwd; subm dgrad (kflip=1, transposed weight strides); Convolution fwd (child
+ * table); Deconvolution dgrad (child table, transposed); NetworkInNetwork fwd/dgrad. */
+int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
+                       int kflip, const int32_t* table, int64_t ld, int K, int64_t n_out_cap,
+                       const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
+                       int math_mode, void* stream);
+
+/* out[p, :] = in[parent[p], :] @ W[kofs[p]]
+ * serves: Deconvolution fwd; Convolution dgrad (transposed weight strides). */
+int b200scn_conv_parent(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
+                        const int32_t* parent, const uint8_t* kofs, int K, int64_t n_out_cap,
+                        const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo, int math_mode,
+                        void* stream);
+
+/* dW[k] (+)= sum_r A[ra(r,k), :]^T @ B[rb(r,k), :]   with, for gather_b == 0,
+ *   ra = table[k][r], rb = r  (subm wgrad: A = in, B = dout;  Convolution wgrad: child table)
+ * and for gather_b == 1,  ra = r, rb = table[k][r]       (Deconvolution wgrad: child table).
+ * dW is dense [K][Ca][Cb].  Deterministic: partial sums per row-chunk land in scratch and
+ * are reduced in fixed order.  table == NULL: K == 1, identity (NetworkInNetwork wgrad). */
+int64_t b200scn_wgrad_scratch_bytes(int64_t n_cap, int K, int Ca, int Cb);
+int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* table,
+                        int64_t ld, int K, int gather_b, int64_t n_cap, const int32_t* n_dev, int Ca, int Cb,
+                        float* dW, int accumulate, int math_mode, void* scratch, int64_t scratch_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (iii) fused BatchNorm + (leaky) ReLU -- scn.BatchNormReLU (uresnet_sparse.py:23) and
+ * scn.BatchNormLeakyReLU inside scn.UNet.  eps inside the sqrt, `retention` is scn's
+ * "momentum" (0.9 keeps 90% of the running value), running_var uses the unbiased variance.
+ * ------------------------------------------------------------------------------------- */
+int64_t b200scn_bn_scratch_bytes(int64_t n_cap, int C);
+int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var,
+                         float eps, float retention, float leak, float* y, int64_t ldy, float* save_mean,
+                         float* save_invstd, void* scratch, int64_t scratch_bytes, void* stream);
+int b200scn_bn_fwd_eval(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
+                        const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float leak, float* y, int64_t ldy, void* stream);
+/* backward of the fused op; the activation mask is recomputed from x and the saved stats.
+ * train != 0: batch-stat backward; train == 0: affine backward with fixed (mean, invstd).
+ * dgamma / dbeta are written (not accumulated). */
+int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t n_cap,
+                   const int32_t* n_dev, int C, const float* gamma, const float* beta, const float* mean,
+                   const float* invstd, float leak, int train, float* dx, int64_t lddx, float* dgamma,
+                   float* dbeta, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (iv) input / output layers -- scn.InputLayer features (mode 3 sums) and scn.OutputLayer
+ * (uresnet_sparse.py:20,24), forward and backward.
+ * ------------------------------------------------------------------------------------- */
+/* dst[i, :] = src[idx[i], :]                        (OutputLayer fwd, InputLayer bwd) */
+int b200scn_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t n_cap, const int32_t* n_dev,
+                        int C, float* dst, int64_t ldd, void* stream);
+/* dst[r, :] = src[first_idx[r], :] + sum_{j in seg[seg_off[r] .. seg_off[r+1])} src[j, :]   in that order
+ *                                                   (InputLayer fwd, OutputLayer bwd) */
+int b200scn_segsum_rows(const float* src, int64_t lds, const int32_t* first_idx, const int32_t* seg_off,
+                        const int32_t* seg, int64_t n_cap, const int32_t* n_dev, int C, float* dst, int64_t ldd,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (v) elementwise helpers used by the table modules (AddTable / JoinTable) and the trainer.
+ * ------------------------------------------------------------------------------------- */
+/* out[r, 0:C] = a[r, 0:C] + b[r, 0:C] */
+int b200scn_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n_cap,
+                     const int32_t* n_dev, int C, float* out, int64_t ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SCN_H */

@@ -1,0 +1,155 @@
+"""Whole sparse U-ResNet: CUDA vs oracle (logits, loss, every gradient), golden fixture,
+static/graph regime vs eager, permutation invariance, trainer."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import small_flags
+from helpers import event_blob, rel_l2
+from oracle.model import OracleUResNet, segmentation_loss
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+LOGIT_TOL = 1e-4   # max|d| <= LOGIT_TOL * max|logit|   (fp32 kernels vs fp32 oracle)
+GRAD_TOL = 2e-3    # rel-L2 per parameter tensor
+
+
+def _models(flags, seed=0):
+    from uresnet_pytorch_b200.model import UResNet
+    torch.manual_seed(seed)
+    ref = OracleUResNet(flags).train()
+    with torch.no_grad():
+        for mod in ref.modules():
+            if hasattr(mod, "running_mean"):
+                mod.weight.uniform_(0.7, 1.3)
+                mod.bias.uniform_(-0.2, 0.2)
+    net = UResNet(flags)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda().train()
+
+
+def _loss_gpu(net, d, l, n_events):
+    from uresnet_pytorch_b200.model import SegmentationLoss
+    crit = SegmentationLoss()
+    crit.num_events = n_events
+    out = net(d)[0]
+    loss, acc = crit([out], [d], [l], None)
+    return out, loss, acc
+
+
+@pytest.mark.parametrize("dim,ss,uf,uns", [(3, 32, 8, 3), (3, 64, 16, 4), (2, 64, 16, 4)])
+def test_model_forward_backward_matches_oracle(dim, ss, uf, uns):
+    flags = small_flags(DATA_DIM=dim, SPATIAL_SIZE=ss, URESNET_FILTERS=uf, URESNET_NUM_STRIDES=uns)
+    ref, net = _models(flags)
+    data, label = event_blob(2, ss, dim=dim, dup=25)
+    d, l = torch.from_numpy(data), torch.from_numpy(label)
+    out_ref = ref(d)[0]
+    loss_ref, acc_ref = segmentation_loss(out_ref, d, l)
+    loss_ref.backward()
+    out, loss, acc = _loss_gpu(net, d.cuda(), l.cuda(), 2)
+    loss.backward()
+    torch.cuda.synchronize()
+    scale = out_ref.abs().max().item()
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= LOGIT_TOL * scale
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    assert abs(float(acc) - acc_ref) < 1e-3
+    g_ref = dict(ref.named_parameters())
+    for name, p in net.named_parameters():
+        assert rel_l2(p.grad, g_ref[name].grad) <= GRAD_TOL, name
+    b_ref = dict(ref.named_buffers())
+    for name, b in net.named_buffers():
+        assert rel_l2(b, b_ref[name]) <= 1e-4, name
+
+
+def test_model_matches_golden_fixture():
+    from uresnet_pytorch_b200.model import UResNet
+    g = np.load(os.path.join(GOLDEN, "sparse_tiny.npz"))
+    flags = small_flags(SPATIAL_SIZE=int(g["ss"]), URESNET_FILTERS=int(g["uf"]), URESNET_NUM_STRIDES=int(g["uns"]))
+    net = UResNet(flags)
+    net.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")})
+    net.cuda().train()
+    d, l = torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["label"]).cuda()
+    out, loss, _ = _loss_gpu(net, d, l, 2)
+    loss.backward()
+    assert np.abs(out.detach().cpu().numpy() - g["logits"]).max() <= LOGIT_TOL * np.abs(g["logits"]).max()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    assert rel_l2(net.sparseModel[1].weight.grad, torch.from_numpy(g["grad_stem"])) <= GRAD_TOL
+    assert rel_l2(net.linear.weight.grad, torch.from_numpy(g["grad_linear"])) <= GRAD_TOL
+    for k in g.files:
+        if k.startswith("after."):
+            assert rel_l2(net.state_dict()[k[6:]], torch.from_numpy(g[k])) <= 1e-4, k
+
+
+def test_permutation_invariance_on_gpu():
+    flags = small_flags()
+    _, net = _models(flags)
+    data, _ = event_blob(2, 32, dup=20)
+    d = torch.from_numpy(data).cuda()
+    with torch.no_grad():
+        out = net(d)[0]
+        perm = torch.randperm(len(d), device="cuda")
+        out_p = net(d[perm])[0]
+    assert (out[perm] - out_p).abs().max().item() <= 1e-4 * out.abs().max().item()
+
+
+def test_eval_mode_and_inference():
+    flags = small_flags()
+    ref, net = _models(flags)
+    data, label = event_blob(1, 32)
+    d = torch.from_numpy(data)
+    ref.eval()
+    net.eval()
+    with torch.no_grad():
+        a = ref(d)[0]
+        b = net(d.cuda())[0]
+    assert (b.cpu() - a).abs().max().item() <= LOGIT_TOL * a.abs().max().item()
+
+
+def test_static_regime_matches_eager_forward_backward():
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    flags = small_flags()
+    _, net = _models(flags)
+    data, label = event_blob(2, 32, dup=10)
+    d, l = torch.from_numpy(data).cuda(), torch.from_numpy(label).cuda()
+    out_e, loss_e, _ = _loss_gpu(net, d, l, 2)
+    loss_e.backward()
+    g_e = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    with scn.static_mode(True):
+        out_s, loss_s, _ = _loss_gpu(net, d, l, 2)
+        loss_s.backward()
+    assert torch.equal(out_s, out_e)
+    for n, p in net.named_parameters():
+        assert torch.equal(p.grad, g_e[n]), n
+
+
+def test_graph_trainer_matches_eager_trainer():
+    """Whole-step CUDA graph (static regime, padded capacity) == eager step, over several
+    steps with different event sizes."""
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    blobs = [event_blob(2, 32, seed=s) for s in (1, 2, 3, 4)]
+    cap = max(len(b[0]) for b in blobs) + 37
+    te = Trainer(flags, lr=1e-3, graph=False, events_per_step=2, seed=5)
+    tg = Trainer(flags, lr=1e-3, graph=True, capacity=cap, events_per_step=2, seed=5)
+    for data, label in blobs:
+        re_ = te.train_step(data, label)
+        rg = tg.train_step(data, label)
+        assert abs(re_["loss"] - rg["loss"]) <= 2e-4 * abs(re_["loss"]), (re_, rg)
+        assert abs(re_["acc"] - rg["acc"]) <= 1e-3
+    for (n, a), (_, b) in zip(te.net.named_parameters(), tg.net.named_parameters()):
+        assert rel_l2(b, a) <= 1e-3, n
+
+
+def test_training_reduces_loss():
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    data, label = event_blob(2, 32, seed=8)
+    t = Trainer(flags, lr=3e-3, graph=False, events_per_step=2, seed=1)
+    first = t.train_step(data, label)["loss"]
+    for _ in range(15):
+        last = t.train_step(data, label)["loss"]
+    assert last < 0.7 * first, (first, last)

@@ -1,0 +1,281 @@
+// Fused sparse BatchNorm + (leaky) ReLU (north-star job 3): scn.BatchNormReLU
+// (/root/reference/uresnet/models/uresnet_sparse.py:23) and the BatchNormLeakyReLU layers
+// inside scn.UNet (:22).  Semantics per SURVEY.md 8(a) row a6 / Appendix A.7.
+//
+// Pure HBM-bound streaming over an [N, C] fp32 matrix.  Training forward = one statistics
+// pass (per-thread shifted sums, merged with Chan's formula in a fixed order so the result
+// is deterministic and as accurate as a two-pass variance) + one apply pass; the per-CTA
+// partials are folded by the last CTA to finish (ticket counter), so no extra launch and no
+// host involvement.  Thread layout: thread = (column c, row lane rl); consecutive threads
+// read consecutive columns of a row -> coalesced for any C.
+#include "common.cuh"
+
+namespace b200scn {
+namespace {
+
+struct Layout {
+  int threads, RL, blocks;
+};
+
+Layout make_layout(int64_t n_cap, int C) {
+  Layout L;
+  L.RL = C >= 256 ? 1 : 256 / C;
+  L.threads = C * L.RL;
+  int64_t b = cdiv(n_cap, 512);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  L.blocks = (int)b;
+  return L;
+}
+
+__device__ __forceinline__ void chan_merge(float& na, float& ma, float& sa, float nb, float mb, float sb) {
+  if (nb == 0.f) return;
+  const float n = na + nb;
+  const float d = mb - ma;
+  ma = ma + d * (nb / n);
+  sa = sa + sb + d * d * (na * nb / n);
+  na = n;
+}
+
+// part layout: [blocks][3][C]  (count, mean, M2)
+__global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                           int C, int RL, float* __restrict__ part, unsigned int* counter, float* running_mean,
+                           float* running_var, float eps, float retention, float* __restrict__ save_mean,
+                           float* __restrict__ save_invstd) {
+  extern __shared__ float sm[];  // [3][threads]
+  __shared__ bool is_last;
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int rpb = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
+
+  float cnt = 0.f, s1 = 0.f, s2 = 0.f, shift = 0.f;
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const float v = __ldg(x + (int64_t)r * ldx + c);
+    if (cnt == 0.f) shift = v;
+    const float d = v - shift;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+    cnt += 1.f;
+  }
+  float mean = 0.f, m2 = 0.f;
+  if (cnt > 0.f) {
+    mean = shift + s1 / cnt;
+    m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+  }
+  sm[t] = cnt;
+  sm[T + t] = mean;
+  sm[2 * T + t] = m2;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) chan_merge(cnt, mean, m2, sm[j * C + c], sm[T + j * C + c], sm[2 * T + j * C + c]);
+    float* p = part + (int64_t)blockIdx.x * 3 * C;
+    p[c] = cnt;
+    p[C + c] = mean;
+    p[2 * C + c] = m2;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (rl == 0) {
+    float N = 0.f, M = 0.f, S = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) {
+      const volatile float* p = part + (int64_t)b * 3 * C;
+      chan_merge(N, M, S, p[c], p[C + c], p[2 * C + c]);
+    }
+    const float var_b = N > 0.f ? S / N : 0.f;
+    save_mean[c] = M;
+    save_invstd[c] = rsqrtf(var_b + eps);
+    if (running_mean != nullptr) {
+      running_mean[c] = retention * running_mean[c] + (1.f - retention) * M;
+      running_var[c] = retention * running_var[c] + (1.f - retention) * (S / fmaxf(N - 1.f, 1.f));
+    }
+  }
+  if (t == 0) *counter = 0u;
+}
+
+__global__ void k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                           int C, int RL, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ mean, const float* __restrict__ invstd_or_var, float eps,
+                           int var_given, float leak, float* __restrict__ y, int64_t ldy) {
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x;
+  const int c = t % C, rl = t / C;
+  float is = invstd_or_var[c];
+  if (var_given) is = rsqrtf(is + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float scale = is * g;
+  const float shift = b - mean[c] * scale;
+  for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
+    float v = fmaf(__ldg(x + (int64_t)r * ldx + c), scale, shift);
+    v = v > 0.f ? v : v * leak;
+    y[(int64_t)r * ldy + c] = v;
+  }
+}
+
+// part layout: [blocks][2][C]
+__global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
+                                int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ mean, const float* __restrict__ invstd, float leak,
+                                float* __restrict__ part, unsigned int* counter, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta) {
+  extern __shared__ float sm[];  // [2][threads]
+  __shared__ bool is_last;
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int rpb = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
+  const float mu = mean[c], is = invstd[c];
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const float xh = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
+    const float yv = fmaf(xh, g, b);
+    float d = __ldg(dy + (int64_t)r * lddy + c);
+    d = yv > 0.f ? d : d * leak;
+    s1 += d;
+    s2 = fmaf(d, xh, s2);
+  }
+  sm[t] = s1;
+  sm[T + t] = s2;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) {
+      s1 += sm[j * C + c];
+      s2 += sm[T + j * C + c];
+    }
+    float* p = part + (int64_t)blockIdx.x * 2 * C;
+    p[c] = s1;
+    p[C + c] = s2;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (rl == 0) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int bk = 0; bk < (int)gridDim.x; ++bk) {
+      const volatile float* p = part + (int64_t)bk * 2 * C;
+      a1 += p[c];
+      a2 += p[C + c];
+    }
+    dbeta[c] = a1;
+    dgamma[c] = a2;
+  }
+  if (t == 0) *counter = 0u;
+}
+
+__global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
+                               int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ invstd, float leak, int train,
+                               const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                               float* __restrict__ dx, int64_t lddx) {
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x;
+  const int c = t % C, rl = t / C;
+  const float mu = mean[c], is = invstd[c];
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  const float k1 = train ? dbeta[c] * inv_n : 0.f;
+  const float k2 = train ? dgamma[c] * inv_n : 0.f;
+  const float gi = g * is;
+  for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
+    const float xh = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
+    const float yv = fmaf(xh, g, b);
+    float d = __ldg(dy + (int64_t)r * lddy + c);
+    d = yv > 0.f ? d : d * leak;
+    dx[(int64_t)r * lddx + c] = gi * (d - k1 - xh * k2);
+  }
+}
+
+int apply_grid(int64_t n_cap, int RL) {
+  int64_t g = cdiv(n_cap, (int64_t)RL * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+}  // namespace b200scn
+
+using namespace b200scn;
+
+extern "C" int64_t b200scn_bn_scratch_bytes(int64_t n_cap, int C) {
+  Layout L = make_layout(n_cap < 1 ? 1 : n_cap, C < 1 ? 1 : C);
+  return 256 + (int64_t)L.blocks * 3 * C * 4;
+}
+
+extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
+                                    const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                    float eps, float retention, float leak, float* y, int64_t ldy, float* save_mean,
+                                    float* save_invstd, void* scratch, int64_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
+  B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_fwd_train: scratch too small");
+  if (n_cap == 0) return 0;
+  Layout L = make_layout(n_cap, C);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
+  B200_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+  k_bn_stats<<<L.blocks, L.threads, 3 * L.threads * sizeof(float), st>>>(
+      x, ldx, n_cap, n_dev, C, L.RL, part, counter, running_mean, running_var, eps, retention, save_mean, save_invstd);
+  k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, save_mean,
+                                                            save_invstd, eps, 0, leak, y, ldy);
+  B200_CHECK_LAUNCH("bn_fwd_train");
+  return 0;
+}
+
+extern "C" int b200scn_bn_fwd_eval(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
+                                   const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, float eps, float leak, float* y, int64_t ldy,
+                                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
+  if (n_cap == 0) return 0;
+  Layout L = make_layout(n_cap, C);
+  k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, running_mean,
+                                                            running_var, eps, 1, leak, y, ldy);
+  B200_CHECK_LAUNCH("bn_fwd_eval");
+  return 0;
+}
+
+extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t n_cap,
+                              const int32_t* n_dev, int C, const float* gamma, const float* beta, const float* mean,
+                              const float* invstd, float leak, int train, float* dx, int64_t lddx, float* dgamma,
+                              float* dbeta, void* scratch, int64_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
+  B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_bwd: scratch too small");
+  if (n_cap == 0) {
+    B200_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
+    B200_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+    return 0;
+  }
+  Layout L = make_layout(n_cap, C);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
+  B200_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+  k_bn_bwd_reduce<<<L.blocks, L.threads, 2 * L.threads * sizeof(float), st>>>(
+      x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta, mean, invstd, leak, part, counter, dgamma, dbeta);
+  k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta,
+                                                                mean, invstd, leak, train, dgamma, dbeta, dx, lddx);
+  B200_CHECK_LAUNCH("bn_bwd");
+  return 0;
+}

@@ -1,0 +1,34 @@
+"""Process-wide switches of the b200 sparseconvnet surface."""
+import contextlib
+
+# B200SCN_MATH_* of include/b200scn.h: 0 = fp32 FFMA, 1 = tf32x3 tensor-core (fp32-equivalent), 2 = tf32
+MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
+math_mode = MATH_FP32
+
+# False: eager regime (exact row counts, one host read-back per level).
+# True : static regime (capacity-sized matrices, device-side row counts, CUDA-graph capturable).
+static_shapes = False
+# static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
+static_input_rows = None
+
+
+@contextlib.contextmanager
+def static_mode(enabled=True):
+    global static_shapes
+    prev = static_shapes
+    static_shapes = enabled
+    try:
+        yield
+    finally:
+        static_shapes = prev
+
+
+@contextlib.contextmanager
+def math(mode):
+    global math_mode
+    prev = math_mode
+    math_mode = mode
+    try:
+        yield
+    finally:
+        math_mode = prev

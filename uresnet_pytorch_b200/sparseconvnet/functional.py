@@ -1,0 +1,224 @@
+"""torch.autograd.Functions over the C-ABI (include/b200scn.h).
+
+Each Function is the forward/dgrad/wgrad triple of one scn layer type used by
+/root/reference/uresnet/models/uresnet_sparse.py:19-24.  They only pass raw device pointers,
+row strides and the current stream; all arithmetic happens in libb200scn.
+"""
+import torch
+
+from .. import _lib
+from . import config
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rowmajor(x):
+    return x if (x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1]) else x.contiguous()
+
+
+def _check_cuda_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("b200 sparseconvnet: tensors must be on a CUDA device (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError("b200 sparseconvnet: features and weights are float32 (got %s)" % t.dtype)
+
+
+def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
+    Ca, Cb = A.shape[1], B.shape[1]
+    L = _lib.load()
+    nbytes = L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
+    _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
+              table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0, math,
+              scratch.data_ptr(), nbytes, _stream())
+    return dW
+
+
+class TableConv(torch.autograd.Function):
+    """out[o] = sum_k x[table[k][o]] @ W[k]; table rows index x.  Used by SubmanifoldConvolution
+    (table = neighbour table, symmetric), Convolution (table = child table) and
+    NetworkInNetwork (table = None)."""
+
+    @staticmethod
+    def forward(ctx, x, W, table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs):
+        _check_cuda_f32(x, W)
+        x = _rowmajor(x)
+        W3 = W if W.dim() == 3 else W.unsqueeze(0)
+        W3 = W3.contiguous()
+        K, Cin, Cout = W3.shape
+        math = config.math_mode
+        out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+        _lib.call("b200scn_conv_table", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1, 0,
+                  _lib.ptr(table), table.stride(0) if table is not None else 0, K, n_out, n_out_dev, Cin, Cout,
+                  out.data_ptr(), out.stride(0), 0, math, _stream())
+        ctx.save_for_backward(x, W3)
+        ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, W3 = ctx.saved_tensors
+        table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, w_shape, math = ctx.misc
+        dout = _rowmajor(dout)
+        K, Cin, Cout = W3.shape
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n_in, Cin), dtype=torch.float32, device=x.device)
+            if table is None or symmetric:
+                # dx[i] = sum_k dout[table[k][i]] @ W[K-1-k]^T   (neighbour table is symmetric)
+                _lib.call("b200scn_conv_table", dout.data_ptr(), dout.stride(0), W3.data_ptr(), Cin * Cout, 1, Cout,
+                          1, _lib.ptr(table), table.stride(0) if table is not None else 0, K, n_in, n_in_dev, Cout,
+                          Cin, dx.data_ptr(), dx.stride(0), 0, math, _stream())
+            else:
+                # strided conv: every fine row has exactly one parent
+                _lib.call("b200scn_conv_parent", dout.data_ptr(), dout.stride(0), W3.data_ptr(), Cin * Cout, 1, Cout,
+                          parent.data_ptr(), kofs.data_ptr(), K, n_in, n_in_dev, Cout, Cin, dx.data_ptr(),
+                          dx.stride(0), math, _stream())
+        if ctx.needs_input_grad[1]:
+            dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math)
+        return dx, dW, None, None, None, None, None, None, None, None
+
+
+class ParentConv(torch.autograd.Function):
+    """out[p] = x[parent[p]] @ W[kofs[p]] (Deconvolution with filter == stride)."""
+
+    @staticmethod
+    def forward(ctx, x, W, parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev):
+        _check_cuda_f32(x, W)
+        x = _rowmajor(x)
+        W3 = W.contiguous()
+        K, Cin, Cout = W3.shape
+        math = config.math_mode
+        out = torch.empty((n_fine, Cout), dtype=torch.float32, device=x.device)
+        _lib.call("b200scn_conv_parent", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1,
+                  parent.data_ptr(), kofs.data_ptr(), K, n_fine, n_fine_dev, Cin, Cout, out.data_ptr(), out.stride(0),
+                  math, _stream())
+        ctx.save_for_backward(x, W3)
+        ctx.misc = (parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, W3 = ctx.saved_tensors
+        parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math = ctx.misc
+        dout = _rowmajor(dout)
+        K, Cin, Cout = W3.shape
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            # dx[j] = sum_k dout[child[k][j]] @ W[k]^T
+            dx = torch.empty((n_coarse, Cin), dtype=torch.float32, device=x.device)
+            _lib.call("b200scn_conv_table", dout.data_ptr(), dout.stride(0), W3.data_ptr(), Cin * Cout, 1, Cout, 0,
+                      child.data_ptr(), child.stride(0), K, n_coarse, n_coarse_dev, Cout, Cin, dx.data_ptr(),
+                      dx.stride(0), 0, math, _stream())
+        if ctx.needs_input_grad[1]:
+            # dW[k] = sum_j x[j]^T @ dout[child[k][j]]
+            dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math)
+        return dx, dW, None, None, None, None, None, None, None
+
+
+class BatchNormAct(torch.autograd.Function):
+    """Fused BatchNorm + leaky ReLU (leak = 0: ReLU, leak = 1: none)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, retention, leak, training, rows, n_dev):
+        _check_cuda_f32(x, weight, bias)
+        x = _rowmajor(x)
+        C = x.shape[1]
+        L = _lib.load()
+        y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+        if training:
+            nbytes = L.b200scn_bn_scratch_bytes(rows, C)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            _lib.call("b200scn_bn_fwd_train", x.data_ptr(), x.stride(0), rows, n_dev, C, _lib.ptr(weight),
+                      _lib.ptr(bias), running_mean.data_ptr(), running_var.data_ptr(), eps, retention, leak,
+                      y.data_ptr(), y.stride(0), mean.data_ptr(), invstd.data_ptr(), scratch.data_ptr(), nbytes,
+                      _stream())
+        else:
+            mean = running_mean
+            invstd = torch.rsqrt(running_var + eps)
+            _lib.call("b200scn_bn_fwd_eval", x.data_ptr(), x.stride(0), rows, n_dev, C, _lib.ptr(weight),
+                      _lib.ptr(bias), running_mean.data_ptr(), running_var.data_ptr(), eps, leak, y.data_ptr(),
+                      y.stride(0), _stream())
+        ctx.save_for_backward(x, weight, bias, mean, invstd)
+        ctx.misc = (leak, training, rows, n_dev)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, invstd = ctx.saved_tensors
+        leak, training, rows, n_dev = ctx.misc
+        dy = _rowmajor(dy)
+        C = x.shape[1]
+        L = _lib.load()
+        nbytes = L.b200scn_bn_scratch_bytes(rows, C)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        dx = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        _lib.call("b200scn_bn_bwd", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), rows, n_dev, C,
+                  _lib.ptr(weight), _lib.ptr(bias), mean.data_ptr(), invstd.data_ptr(), leak, int(training),
+                  dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(), nbytes,
+                  _stream())
+        return (dx, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
+                None, None, None, None, None)
+
+
+class InputGather(torch.autograd.Function):
+    """InputLayer mode 3: active row = sum of its input points, in input order."""
+
+    @staticmethod
+    def forward(ctx, feats, md, rows, n_dev):
+        _check_cuda_f32(feats)
+        feats = _rowmajor(feats)
+        C = feats.shape[1]
+        out = torch.empty((rows, C), dtype=torch.float32, device=feats.device)
+        _lib.call("b200scn_segsum_rows", feats.data_ptr(), feats.stride(0), md.first_idx.data_ptr(),
+                  md.seg_off.data_ptr(), md.seg.data_ptr(), rows, n_dev, C, out.data_ptr(), out.stride(0), _stream())
+        ctx.md = md
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        md = ctx.md
+        dout = _rowmajor(dout)
+        C = dout.shape[1]
+        din = torch.empty((md.n_in, C), dtype=torch.float32, device=dout.device)
+        _lib.call("b200scn_gather_rows", dout.data_ptr(), dout.stride(0), md.in2row.data_ptr(), md.n_in,
+                  _lib.ptr(md.n_in_dev), C, din.data_ptr(), din.stride(0), _stream())
+        return din, None, None, None
+
+
+class OutputGather(torch.autograd.Function):
+    """OutputLayer: every original input point receives its active row."""
+
+    @staticmethod
+    def forward(ctx, feats, md, rows, n_dev):
+        _check_cuda_f32(feats)
+        feats = _rowmajor(feats)
+        C = feats.shape[1]
+        # padded rows (static regime) must hold finite values: the head and the loss read them
+        alloc = torch.zeros if md.n_in_dev is not None else torch.empty
+        out = alloc((md.n_in, C), dtype=torch.float32, device=feats.device)
+        _lib.call("b200scn_gather_rows", feats.data_ptr(), feats.stride(0), md.in2row.data_ptr(), md.n_in,
+                  _lib.ptr(md.n_in_dev), C, out.data_ptr(), out.stride(0), _stream())
+        ctx.md, ctx.rows, ctx.n_dev = md, rows, n_dev
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        md = ctx.md
+        dout = _rowmajor(dout)
+        C = dout.shape[1]
+        d = torch.empty((ctx.rows, C), dtype=torch.float32, device=dout.device)
+        _lib.call("b200scn_segsum_rows", dout.data_ptr(), dout.stride(0), md.first_idx.data_ptr(),
+                  md.seg_off.data_ptr(), md.seg.data_ptr(), ctx.rows, ctx.n_dev, C, d.data_ptr(), d.stride(0),
+                  _stream())
+        return d, None, None, None
