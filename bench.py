@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- sparse U-ResNet train voxels/sec at 512^3 on N B200s (+ subm-conv HBM GB/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle port on host cores
+
+One "step" = one full training step (rulebook build, forward, loss, backward, gradient
+all-reduce, Adam) on one batch of synthetic LArTPC-like events per GPU -- BASELINE.json
+configs[1]: uresnet_sparse 3D, ss=512, uns=5, uf=16, nc=5, bs=1 (README command of the
+reference).  Weak scaling: every rank processes `--events-per-gpu` events per step.
+
+Timing: W >= 3 warm-up steps, then K steps each bracketed by CUDA events on the launching
+stream with a 256 MB L2 flush between steps (outside the events); barrier +
+torch.cuda.synchronize() on both sides; MAX over ranks.  `value` = steps on inputs already
+resident in HBM; `e2e` = the same metric through Trainer.train_step(host blob) with the
+pinned H2D copy of the float64 blob and the D2H read of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIG = dict(ss=512, uns=5, uf=16, nc=5, dim=3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--events-per-gpu", type=int, default=1)
+    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic steps cycled through")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-events", type=int, default=128)
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pool(args, rank):
+    from uresnet_pytorch_b200 import synthetic
+    stream = synthetic.EventStream(args.events_per_gpu, CONFIG["ss"], CONFIG["dim"], rank=rank)
+    return [stream.next() for _ in range(args.pool)]
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_step_time(n_steps, events_per_step, threads):
+    """The oracle port (oracle/, torch-CPU restatement of scn's per-offset gather/mm/scatter)
+    timed on host cores: full train steps of the same workload.  Baseline only."""
+    import torch
+    from oracle.model import OracleUResNet, segmentation_loss
+    from uresnet_pytorch_b200 import synthetic
+    from uresnet_pytorch_b200.model import Flags
+    torch.set_num_threads(threads)
+    flags = Flags(DATA_DIM=CONFIG["dim"], SPATIAL_SIZE=CONFIG["ss"], URESNET_FILTERS=CONFIG["uf"],
+                  URESNET_NUM_STRIDES=CONFIG["uns"], NUM_CLASS=CONFIG["nc"])
+    torch.manual_seed(0)
+    net = OracleUResNet(flags).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    stream = synthetic.EventStream(events_per_step, CONFIG["ss"], CONFIG["dim"])
+    times, vox = [], []
+    for i in range(n_steps + 1):
+        data, label = stream.next()
+        d, l = torch.from_numpy(data), torch.from_numpy(label)
+        t0 = time.perf_counter()
+        out = net(d)[0]
+        loss, _ = segmentation_loss(out, d, l)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i > 0:  # first step warms the allocator / thread pool
+            times.append(dt)
+            vox.append(len(data))
+    return times, vox
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 5))
+    times, vox = cpu_oracle_step_time(steps, args.events_per_gpu, threads)
+    total_t, total_v = sum(times), sum(vox)
+    value = total_v / total_t
+    line = {
+        "impl": "reference", "metric": "sparse U-ResNet train voxels/sec at 512^3", "value": value,
+        "unit": "voxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d (BASELINE configs[1])"
+                               % args.events_per_gpu},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
+                         "sample": "%d full train steps (1 untimed) of the CPU oracle port "
+                                   "(scn is not installable here, so the port stands in for the reference's CPU "
+                                   "path), requested steps clamped to 5" % steps},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def subm_roofline(args, math_mode):
+    """subm-conv HBM GB/s on a batch large enough to exceed L2: level-0
+    SubmanifoldConvolution 16->16 over `--roofline-events` concatenated 512^3 events, timed with
+    CUDA events on the launching stream, L2 flushed between launches."""
+    import torch
+    from uresnet_pytorch_b200 import _lib, synthetic
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+    dev = torch.device("cuda")
+    data, _, _ = synthetic.make_batch(args.roofline_events, CONFIG["ss"], CONFIG["dim"], seed=4321)
+    coords = torch.from_numpy(data[:, :4]).to(dev)
+    md = Metadata(3)
+    size = (CONFIG["ss"],) * 3
+    lv = md.set_input(coords, size)
+    nbr = md.subm_table(size, 3)
+    n, C, K = lv.n, CONFIG["uf"], 27
+    torch.manual_seed(0)
+    x = torch.randn(n, C, device=dev)
+    W = torch.randn(K, C, C, device=dev) * 0.05
+    out = torch.empty(n, C, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    pairs = int((nbr[:, :n] >= 0).sum().item())
+
+    def launch():
+        _lib.call("b200scn_conv_table", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, nbr.data_ptr(), nbr.stride(0),
+                  K, n, None, C, C, out.data_ptr(), C, 0, math_mode, st.cuda_stream)
+
+    for _ in range(3):
+        launch()
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        launch()
+        e1.record(st)
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.mean(times)
+    # algorithmic bytes: s*(N*Cin + N*Cout) + 4*K*N + s*K*Cin*Cout
+    alg = 4 * (n * C + n * C) + 4 * K * n + 4 * K * C * C
+    peak, src = peaks()
+    return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
+            "traffic": None, "peak_source": src, "kernel": "b200scn_conv_table (subm 3^3, 16->16, fwd)",
+            "workload": "%d events of 512^3 concatenated: %d active sites, %d rule pairs (working set > L2)"
+                        % (args.roofline_events, n, pairs),
+            "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3, "gflops": 2.0 * pairs * C * C / t / 1e9}
+
+
+def run_b200(args):
+    import torch
+    from uresnet_pytorch_b200 import _lib
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.model import Flags
+    from uresnet_pytorch_b200.trainer import Trainer, init_distributed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference)")
+    rank, local, world = init_distributed()
+    dist = torch.distributed if world > 1 else None
+    dev = torch.device("cuda", local)
+    math_mode = {"fp32": scn.MATH_FP32, "tf32x3": scn.MATH_TF32X3, "tf32": scn.MATH_TF32}[args.math]
+    flags = Flags(DATA_DIM=CONFIG["dim"], SPATIAL_SIZE=CONFIG["ss"], URESNET_FILTERS=CONFIG["uf"],
+                  URESNET_NUM_STRIDES=CONFIG["uns"], NUM_CLASS=CONFIG["nc"])
+    pool = make_pool(args, rank)
+    cap = max(len(d) for d, _ in pool)
+    cap = ((cap + cap // 8 + 4095) // 4096) * 4096
+    graph = not args.no_graph
+    trainer = Trainer(flags, lr=1e-3, graph=graph, capacity=cap if graph else None,
+                      events_per_step=args.events_per_gpu, math_mode=math_mode, seed=0)
+    launches0 = _lib.load().b200scn_launch_count()
+    r = trainer.train_step(*pool[0])  # builds / captures the graph
+    launches_capture = _lib.load().b200scn_launch_count() - launches0
+    assert np.isfinite(r["loss"]), r
+
+    # device-resident copies of the pool (inputs in HBM before the timed region starts)
+    dpool = []
+    for d, l in pool:
+        n = len(d)
+        dd = torch.from_numpy(d).to(dev)
+        ll = torch.from_numpy(l).to(dev)
+        dpool.append((dd, ll, torch.tensor([n], dtype=torch.int32, device=dev), n))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+
+    def resident_step(i):
+        dd, ll, nn, n = dpool[i % len(dpool)]
+        if graph:
+            trainer.d_data[:n].copy_(dd)
+            trainer.d_label[:n].copy_(ll)
+            trainer.d_n.copy_(nn)
+            trainer.step_resident()
+        else:
+            trainer.step_resident(dd, ll)
+        return n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # per-replay launch count (graph: what one replay contains; eager: measured per step)
+    l0 = _lib.load().b200scn_launch_count()
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    torch.cuda.synchronize()
+    per_step_eager = (_lib.load().b200scn_launch_count() - l0) / max(args.warmup, 3)
+    per_step_launches = int(round(launches_capture / 4.0)) if graph else int(round(per_step_eager))
+    # (graph mode: train_step ran 3 eager warm-up steps + 1 captured step => capture count / 4)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev, vox = [], 0
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        vox += resident_step(i)
+        e1.record(st)
+        ev.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end: host blob -> pinned -> H2D -> step -> D2H loss, wall clock
+    for i in range(3):
+        trainer.train_step(*pool[i % len(pool)])
+    barrier()
+    t0 = time.perf_counter()
+    vox_e2e, h2d = 0, 0
+    for i in range(args.steps):
+        d, l = pool[i % len(pool)]
+        trainer.train_step(d, l)
+        vox_e2e += len(d)
+        h2d += d.nbytes + l.nbytes + 4
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    tt = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device=dev)
+    vv = torch.tensor([vox, vox_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vv, op=dist.ReduceOp.SUM)
+    dev_s, e2e_s, wall = tt.tolist()
+    vox_all, vox_e2e_all = vv.tolist()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+        return
+
+    roof = None
+    if not args.no_roofline:
+        try:
+            roof = subm_roofline(args, math_mode)
+        except Exception as e:  # keep the headline line even if the microbench cannot run
+            roof = {"bound": "hbm", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None,
+                    "traffic": None, "error": repr(e)}
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        times, cv = cpu_oracle_step_time(3, args.events_per_gpu, threads)
+        cpu = {"value": sum(cv) / sum(times), "unit": "voxels/s", "cores": threads, "kind": "port",
+               "sample": "3 full train steps (after 1 untimed) of the CPU oracle port on the same workload "
+                         "(bs=%d, 512^3); %.2f s/step" % (args.events_per_gpu, sum(times) / len(times))}
+
+    line = {
+        "metric": "sparse U-ResNet train voxels/sec at 512^3", "value": vox_all / dev_s, "unit": "voxels/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (tf32x3 mma)", "tf32": "tf32"}[args.math], "data": "synthetic",
+        "config": {"workload": "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[1]), "
+                               "Adam, fp32" % args.events_per_gpu,
+                   "events_per_gpu": args.events_per_gpu, "mean_voxels_per_step_per_gpu": vox_all / world / args.steps,
+                   "cuda_graph": graph, "row_capacity": cap if graph else None,
+                   "l2": "256 MB buffer written between timed steps (L2 flush), outside the CUDA events",
+                   "timing": "sum of per-step CUDA-event durations, max over ranks", "wall_s": wall},
+        "e2e": {"value": vox_e2e_all / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "how": "Trainer.train_step(host float64 blob, float32 labels): pinned staging + H2D + step + "
+                       "D2H of (loss, acc); wall clock, barrier+sync both sides, max over ranks"},
+        "gpu_launches": per_step_launches * args.steps,
+        "gpu_launches_per_step": per_step_launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

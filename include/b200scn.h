@@ -51,6 +51,8 @@ extern "C" {
 
 const char* b200scn_last_error(void);
 int b200scn_version(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches evidence) */
+int64_t b200scn_launch_count(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int b200scn_sm_count(void);
 

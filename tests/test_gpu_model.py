@@ -121,9 +121,10 @@ def test_static_regime_matches_eager_forward_backward():
     with scn.static_mode(True):
         out_s, loss_s, _ = _loss_gpu(net, d, l, 2)
         loss_s.backward()
-    assert torch.equal(out_s, out_e)
+    # same kernels, but capacity-sized grids change the (fixed) reduction split: round-off only
+    assert (out_s - out_e).abs().max().item() <= 1e-5 * out_e.abs().max().item()
     for n, p in net.named_parameters():
-        assert torch.equal(p.grad, g_e[n]), n
+        assert rel_l2(p.grad, g_e[n]) <= 1e-4, n
 
 
 def test_graph_trainer_matches_eager_trainer():

@@ -16,6 +16,7 @@ SIGNATURES = {
     "b200scn_last_error": (_c.c_char_p, []),
     "b200scn_version": (_I32, []),
     "b200scn_sm_count": (_I32, []),
+    "b200scn_launch_count": (_I64, []),
     "b200scn_hash_slots": (_I64, [_I64]),
     "b200scn_rulebook_scratch_bytes": (_I64, [_I64]),
     "b200scn_input_build": (_I32, [_P, _I32, _I64, _I32, _I32, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P,

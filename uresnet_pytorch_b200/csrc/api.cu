@@ -1,11 +1,16 @@
 // libb200scn: error plumbing, device queries and the math-mode dispatch of the conv entry points.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200scn {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -46,6 +51,7 @@ using namespace b200scn;
 
 extern "C" const char* b200scn_last_error(void) { return g_err; }
 extern "C" int b200scn_version(void) { return 1; }
+extern "C" int64_t b200scn_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int b200scn_sm_count(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {

@@ -238,6 +238,7 @@ extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, 
       x, ldx, n_cap, n_dev, C, L.RL, part, counter, running_mean, running_var, eps, retention, save_mean, save_invstd);
   k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, save_mean,
                                                             save_invstd, eps, 0, leak, y, ldy);
+  count_launches(2);
   B200_CHECK_LAUNCH("bn_fwd_train");
   return 0;
 }
@@ -252,6 +253,7 @@ extern "C" int b200scn_bn_fwd_eval(const float* x, int64_t ldx, int64_t n_cap, c
   Layout L = make_layout(n_cap, C);
   k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, running_mean,
                                                             running_var, eps, 1, leak, y, ldy);
+  count_launches(1);
   B200_CHECK_LAUNCH("bn_fwd_eval");
   return 0;
 }
@@ -276,6 +278,7 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
       x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta, mean, invstd, leak, part, counter, dgamma, dbeta);
   k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta,
                                                                 mean, invstd, leak, train, dgamma, dbeta, dx, lddx);
+  count_launches(2);
   B200_CHECK_LAUNCH("bn_bwd");
   return 0;
 }

@@ -37,6 +37,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+void count_launches(int n);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

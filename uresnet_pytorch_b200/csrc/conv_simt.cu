@@ -150,6 +150,7 @@ int conv_rows_dispatch(const float* in, int64_t ldi, const float* W, int64_t w_s
       default: B200_ROWS(8); break;
     }
 #undef B200_ROWS
+    count_launches(1);
   }
   B200_CHECK_LAUNCH("conv_rows");
   return 0;
@@ -315,6 +316,7 @@ int wgrad_table_simt(const float* A, int64_t lda, const float* B, int64_t ldb, c
   if (g > 1024) g = 1024;
   k_wgrad_reduce<<<(int)g, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), elems, rps, ns, n_cap, n_dev, dW,
                                          accumulate);
+  count_launches(2);
   B200_CHECK_LAUNCH("wgrad_table");
   return 0;
 }

@@ -64,6 +64,7 @@ extern "C" int b200scn_gather_rows(const float* src, int64_t lds, const int32_t*
   B200_CHECK_ARG(C >= 1, "gather_rows: C must be >= 1");
   if (n_cap == 0) return 0;
   k_gather_rows<<<ew_grid(n_cap * C), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, n_cap, n_dev, C, dst, ldd);
+  count_launches(1);
   B200_CHECK_LAUNCH("gather_rows");
   return 0;
 }
@@ -75,6 +76,7 @@ extern "C" int b200scn_segsum_rows(const float* src, int64_t lds, const int32_t*
   if (n_cap == 0) return 0;
   k_segsum_rows<<<ew_grid(n_cap * C), 256, 0, (cudaStream_t)stream>>>(src, lds, first_idx, seg_off, seg, n_cap, n_dev,
                                                                       C, dst, ldd);
+  count_launches(1);
   B200_CHECK_LAUNCH("segsum_rows");
   return 0;
 }
@@ -84,6 +86,7 @@ extern "C" int b200scn_add_rows(const float* a, int64_t lda, const float* b, int
   B200_CHECK_ARG(C >= 1, "add_rows: C must be >= 1");
   if (n_cap == 0) return 0;
   k_add_rows<<<ew_grid(n_cap * C), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n_cap, n_dev, C, out, ldo);
+  count_launches(1);
   B200_CHECK_LAUNCH("add_rows");
   return 0;
 }

@@ -197,6 +197,7 @@ int scan_i32(const int32_t* in, int32_t* out, int64_t n_cap, const int32_t* n_de
   k_scan_blocksums<<<nb, kScanBlock, 0, st>>>(in, n_cap, n_dev, bsums);
   k_scan_sums<<<1, kScanBlock, 0, st>>>(bsums, n_cap, n_dev, total_out, end_out);
   k_scan_apply<<<nb, kScanBlock, 0, st>>>(in, n_cap, n_dev, bsums, out);
+  count_launches(3);
   B200_CHECK_LAUNCH("scan_i32");
   return 0;
 }
@@ -393,6 +394,7 @@ extern "C" int b200scn_input_build(const void* coords, int coord_dtype, int64_t 
   if (int rc = scan_i32(s.cnt, seg_off, n_cap, n_act_dev, nullptr, seg_off, s.bsums, st)) return rc;
   k_dup_fill<<<g, blk, 0, st>>>(s.flags, in2row, n_cap, n_dev, seg_off, s.cur, seg);
   k_dup_sort<<<g, blk, 0, st>>>(seg_off, n_cap, n_act_dev, seg);
+  count_launches(7);
   B200_CHECK_LAUNCH("input_build");
   return 0;
 }
@@ -424,6 +426,7 @@ extern "C" int b200scn_level_down(const uint64_t* ukeys, int64_t n_cap, const in
   if (int rc = scan_i32(s.flags, s.ranks, n_cap, n_dev, n_next_dev, nullptr, s.bsums, st)) return rc;
   k_assign_rows<<<g, blk, 0, st>>>(s.flags, s.ranks, s.slot_of, s.keys, n_cap, n_dev, tvals, ukeys_next, nullptr);
   k_parent_child<<<g, blk, 0, st>>>(tvals, s.slot_of, kofs, n_cap, n_dev, parent, child, ld_child);
+  count_launches(4);
   B200_CHECK_LAUNCH("level_down");
   return 0;
 }
@@ -443,6 +446,7 @@ extern "C" int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const in
   const int blk = 256;
   dim3 grid(grid_for(n_cap, blk), K / 2 + 1);
   k_subm_table<<<grid, blk, 0, st>>>(ukeys, n_cap, n_dev, D, k, K, tkeys, tvals, (uint64_t)slots - 1, nbr, ld);
+  count_launches(1);
   B200_CHECK_LAUNCH("subm_table");
   return 0;
 }
