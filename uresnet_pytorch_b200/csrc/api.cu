@@ -41,9 +41,16 @@ int64_t wgrad_scratch_bytes_simt(int64_t, int, int, int);
 int wgrad_table_simt(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
                      const int32_t*, int, int, float*, int, void*, int64_t, cudaStream_t);
 // conv_mma.cu
-bool conv_table_mma_supported(int Cin, int Cout, int K, int64_t ldi, int64_t ldo, const void* in, const void* out);
-int conv_table_mma(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t, int,
-                   int64_t, const int32_t*, int, int, float*, int64_t, int, int, cudaStream_t);
+bool conv_mma_supported(int Cin, int Cout, int K, int64_t ldi, const void* in);
+int conv_rows_mma(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t,
+                  const int32_t*, const uint8_t*, int, int64_t, const int32_t*, int, int, float*, int64_t, int, int,
+                  cudaStream_t);
+
+// wgrad_mma.cu
+bool wgrad_mma_supported(int64_t, int, int, int, int64_t, int64_t, const void*, const void*);
+int64_t wgrad_scratch_bytes_mma(int64_t, int, int, int);
+int wgrad_table_mma(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
+                    const int32_t*, int, int, float*, int, int, void*, int64_t, cudaStream_t);
 
 }  // namespace b200scn
 
@@ -70,9 +77,9 @@ extern "C" int b200scn_conv_table(const float* in, int64_t ldi, const float* W, 
   B200_CHECK_ARG(table == nullptr || ld >= n_out_cap, "conv_table: ld < n_out_cap");
   B200_CHECK_ARG(ldi >= Cin && ldo >= Cout, "conv_table: row stride smaller than channel count");
   B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "conv_table: bad math mode %d", math_mode);
-  if (math_mode != B200SCN_MATH_FP32 && conv_table_mma_supported(Cin, Cout, K, ldi, ldo, in, out))
-    return conv_table_mma(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, K, n_out_cap, n_out_dev, Cin, Cout, out, ldo,
-                          accumulate, math_mode, (cudaStream_t)stream);
+  if (math_mode != B200SCN_MATH_FP32 && conv_mma_supported(Cin, Cout, K, ldi, in))
+    return conv_rows_mma(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, nullptr, nullptr, K, n_out_cap, n_out_dev,
+                         Cin, Cout, out, ldo, accumulate, math_mode, (cudaStream_t)stream);
   return conv_table_simt(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, K, n_out_cap, n_out_dev, Cin, Cout, out, ldo,
                          accumulate, (cudaStream_t)stream);
 }
@@ -84,13 +91,17 @@ extern "C" int b200scn_conv_parent(const float* in, int64_t ldi, const float* W,
   B200_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "conv_parent: bad shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
   B200_CHECK_ARG(parent != nullptr && kofs != nullptr, "conv_parent: parent/kofs must not be NULL");
   B200_CHECK_ARG(ldi >= Cin && ldo >= Cout, "conv_parent: row stride smaller than channel count");
-  (void)math_mode;
+  B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "conv_parent: bad math mode %d", math_mode);
+  if (math_mode != B200SCN_MATH_FP32 && conv_mma_supported(Cin, Cout, K, ldi, in))
+    return conv_rows_mma(in, ldi, W, w_sk, w_si, w_so, 0, nullptr, 0, parent, kofs, K, n_out_cap, n_out_dev, Cin, Cout,
+                         out, ldo, 0, math_mode, (cudaStream_t)stream);
   return conv_parent_simt(in, ldi, W, w_sk, w_si, w_so, parent, kofs, K, n_out_cap, n_out_dev, Cin, Cout, out, ldo,
                           (cudaStream_t)stream);
 }
 
 extern "C" int64_t b200scn_wgrad_scratch_bytes(int64_t n_cap, int K, int Ca, int Cb) {
-  return wgrad_scratch_bytes_simt(n_cap, K, Ca, Cb);
+  const int64_t a = wgrad_scratch_bytes_simt(n_cap, K, Ca, Cb), b = wgrad_scratch_bytes_mma(n_cap, K, Ca, Cb);
+  return a > b ? a : b;
 }
 
 extern "C" int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* table,
@@ -100,7 +111,10 @@ extern "C" int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, 
   B200_CHECK_ARG(Ca >= 1 && Cb >= 1 && K >= 1, "wgrad_table: bad shape Ca=%d Cb=%d K=%d", Ca, Cb, K);
   B200_CHECK_ARG(table != nullptr || K == 1, "wgrad_table: table == NULL requires K == 1");
   B200_CHECK_ARG(lda >= Ca && ldb >= Cb, "wgrad_table: row stride smaller than channel count");
-  (void)math_mode;
+  B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "wgrad_table: bad math mode %d", math_mode);
+  if (math_mode != B200SCN_MATH_FP32 && wgrad_mma_supported(n_cap, K, Ca, Cb, lda, ldb, A, B))
+    return wgrad_table_mma(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, math_mode,
+                           scratch, scratch_bytes, (cudaStream_t)stream);
   return wgrad_table_simt(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, scratch,
                           scratch_bytes, (cudaStream_t)stream);
 }

@@ -21,7 +21,7 @@ Layout make_layout(int64_t n_cap, int C) {
   Layout L;
   L.RL = C >= 256 ? 1 : 256 / C;
   L.threads = C * L.RL;
-  int64_t b = cdiv(n_cap, 512);
+  int64_t b = cdiv(n_cap, 128);
   const int64_t cap = (int64_t)sm_count() * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -52,10 +52,10 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
   const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
 
   float cnt = 0.f, s1 = 0.f, s2 = 0.f, shift = 0.f;
+  if (r0 + rl < r1) shift = __ldg(x + (int64_t)(r0 + rl) * ldx + c);
+#pragma unroll 4
   for (int r = r0 + rl; r < r1; r += RL) {
-    const float v = __ldg(x + (int64_t)r * ldx + c);
-    if (cnt == 0.f) shift = v;
-    const float d = v - shift;
+    const float d = __ldg(x + (int64_t)r * ldx + c) - shift;
     s1 += d;
     s2 = fmaf(d, d, s2);
     cnt += 1.f;
@@ -138,6 +138,7 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
   const float mu = mean[c], is = invstd[c];
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
   for (int r = r0 + rl; r < r1; r += RL) {
     const float xh = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
     const float yv = fmaf(xh, g, b);
