@@ -1,0 +1,100 @@
+"""Tensor-core (mma.sync TF32) kernels vs the CPU oracle.
+
+MATH_TF32X3 (3-term operand split) must be fp32-equivalent: same tolerances as the FFMA
+kernels.  MATH_TF32 (single pass, 10-bit mantissa operands) is the reduced-precision mode:
+max|d| <= 5e-3 * scale on outputs, rel-L2 <= 1e-2 on gradients."""
+import pytest
+import torch
+
+from conftest import small_flags
+from helpers import event_blob, rel_l2
+from oracle import scn_cpu as ocn
+from oracle.model import OracleUResNet, segmentation_loss
+from test_gpu_layers import _check, _lift, _pair
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: (3e-5, 2e-4), 2: (5e-3, 1e-2)}  # math mode -> (forward, gradient)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("dim,cin,cout", [(3, 16, 16), (3, 32, 16), (3, 32, 32), (3, 48, 48), (3, 64, 64),
+                                          (3, 16, 48), (2, 16, 32), (3, 96, 48)])
+def test_submanifold_convolution_mma(mode, dim, cin, cout):
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    x_o, x_g, f_o, f_g = _pair(dim, 24, dup=15)
+    x_o, x_g = _lift(x_o, x_g, f_o, f_g, cin)
+    torch.manual_seed(2)
+    with scn.math(mode):
+        _check(ocn.SubmanifoldConvolution(dim, cin, cout, 3, False),
+               scn.SubmanifoldConvolution(dim, cin, cout, 3, False), x_o, x_g, f_o, f_g, *TOL[mode])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("dim,cin,cout", [(3, 16, 32), (3, 64, 80), (2, 32, 48)])
+def test_strided_mma(mode, dim, cin, cout):
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    x_o, x_g, f_o, f_g = _pair(dim, 24, dup=15)
+    x_o, x_g = _lift(x_o, x_g, f_o, f_g, cin)
+    torch.manual_seed(2)
+    seq_o = ocn.Sequential().add(ocn.Convolution(dim, cin, cout, 2, 2, False)).add(
+        ocn.Deconvolution(dim, cout, cin, 2, 2, False))
+    seq_g = scn.Sequential().add(scn.Convolution(dim, cin, cout, 2, 2, False)).add(
+        scn.Deconvolution(dim, cout, cin, 2, 2, False))
+    with scn.math(mode):
+        _check(seq_o, seq_g, x_o, x_g, f_o, f_g, *TOL[mode])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_network_in_network_mma(mode):
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    x_o, x_g, f_o, f_g = _pair(3, 24)
+    x_o, x_g = _lift(x_o, x_g, f_o, f_g, 32)
+    torch.manual_seed(2)
+    with scn.math(mode):
+        _check(ocn.NetworkInNetwork(32, 16, False), scn.NetworkInNetwork(32, 16, False), x_o, x_g, f_o, f_g,
+               *TOL[mode])
+
+
+@pytest.mark.parametrize("mode,logit_tol,grad_tol", [(1, 1e-4, 2e-3), (2, 2e-2, 5e-2)])
+def test_model_mma_matches_oracle(mode, logit_tol, grad_tol):
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from test_gpu_model import _loss_gpu, _models
+    flags = small_flags(SPATIAL_SIZE=64, URESNET_FILTERS=16, URESNET_NUM_STRIDES=4)
+    ref, net = _models(flags)
+    data, label = event_blob(2, 64, dup=25)
+    d, l = torch.from_numpy(data), torch.from_numpy(label)
+    out_ref = ref(d)[0]
+    loss_ref, _ = segmentation_loss(out_ref, d, l)
+    loss_ref.backward()
+    with scn.math(mode):
+        out, loss, _ = _loss_gpu(net, d.cuda(), l.cuda(), 2)
+        loss.backward()
+    torch.cuda.synchronize()
+    scale = out_ref.abs().max().item()
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= logit_tol * scale
+    g_ref = dict(ref.named_parameters())
+    for name, p in net.named_parameters():
+        assert rel_l2(p.grad, g_ref[name].grad) <= grad_tol, name
+
+
+def test_mma_large_batch_against_fp32_kernel():
+    """BASELINE-size check: tf32x3 tensor-core conv == FFMA conv on a 512^3 multi-event batch."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    data, _ = event_blob(8, 512, seed=2)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    torch.manual_seed(0)
+    feats = torch.randn(len(data), 1, device="cuda")
+    x = scn.InputLayer(3, 512, mode=3)((coords, feats))
+    lift = scn.NetworkInNetwork(1, 16, False).cuda()
+    conv = scn.SubmanifoldConvolution(3, 16, 16, 3, False).cuda()
+    with torch.no_grad():
+        h = lift(x)
+        with scn.math(0):
+            a = conv(h).features
+        with scn.math(1):
+            b = conv(h).features
+        with scn.math(2):
+            c = conv(h).features
+    assert (a - b).abs().max().item() <= 2e-5 * a.abs().max().item()
+    assert (a - c).abs().max().item() <= 5e-3 * a.abs().max().item()
