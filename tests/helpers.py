@@ -39,3 +39,23 @@ def table_as_set(table, n):
     t = table[:, :n].cpu().numpy()
     ks, outs = np.nonzero(t >= 0)
     return set((int(k), int(t[k, o]), int(o)) for k, o in zip(ks, outs))
+
+
+def check_grads(net, ref, global_tol, tensor_tol):
+    """Gradient parity of two models with identical parameter names.
+
+    Deep BN+ReLU stacks amplify round-off (a 1e-7 perturbation can flip a ReLU mask), and
+    tensors whose gradient nearly cancels have a large *relative* error for a tiny absolute
+    one; so the primary bound is the relative L2 error of the whole flattened gradient, with
+    a looser per-tensor bound as a guard against a single broken layer."""
+    import torch
+    g_ref = dict(ref.named_parameters())
+    num = den = 0.0
+    for name, p in net.named_parameters():
+        a, b = p.grad.detach().double().cpu(), g_ref[name].grad.detach().double()
+        num += (a - b).pow(2).sum().item()
+        den += b.pow(2).sum().item()
+        assert rel_l2(a, b) <= tensor_tol, "%s: rel-L2 %g" % (name, rel_l2(a, b))
+    glob = (num / max(den, 1e-300)) ** 0.5
+    assert glob <= global_tol, "global gradient rel-L2 %g" % glob
+    return glob

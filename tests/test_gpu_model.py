@@ -7,14 +7,15 @@ import pytest
 import torch
 
 from conftest import small_flags
-from helpers import event_blob, rel_l2
+from helpers import check_grads, event_blob, rel_l2
 from oracle.model import OracleUResNet, segmentation_loss
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 LOGIT_TOL = 1e-4   # max|d| <= LOGIT_TOL * max|logit|   (fp32 kernels vs fp32 oracle)
-GRAD_TOL = 2e-3    # rel-L2 per parameter tensor
+GRAD_TOL = 1e-3    # rel-L2 of the whole flattened gradient
+TENSOR_TOL = 2e-2  # rel-L2 per parameter tensor (guard; see helpers.check_grads)
 
 
 def _models(flags, seed=0):
@@ -56,9 +57,7 @@ def test_model_forward_backward_matches_oracle(dim, ss, uf, uns):
     assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= LOGIT_TOL * scale
     assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
     assert abs(float(acc) - acc_ref) < 1e-3
-    g_ref = dict(ref.named_parameters())
-    for name, p in net.named_parameters():
-        assert rel_l2(p.grad, g_ref[name].grad) <= GRAD_TOL, name
+    check_grads(net, ref, GRAD_TOL, TENSOR_TOL)
     b_ref = dict(ref.named_buffers())
     for name, b in net.named_buffers():
         assert rel_l2(b, b_ref[name]) <= 1e-4, name
