@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic steps cycled through")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="keep wgrad kernels on the main stream")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-events", type=int, default=128)
     ap.add_argument("--math", default="fp32", choices=["fp32", "tf32x3", "tf32"])
@@ -239,7 +240,8 @@ def run_b200(args):
     cap = ((cap + cap // 8 + 4095) // 4096) * 4096
     graph = not args.no_graph
     trainer = Trainer(flags, lr=1e-3, graph=graph, capacity=cap if graph else None,
-                      events_per_step=args.events_per_gpu, math_mode=math_mode, seed=0)
+                      events_per_step=args.events_per_gpu, math_mode=math_mode, seed=0,
+                      overlap_wgrad=not args.no_overlap)
     launches0 = _lib.load().b200scn_launch_count()
     r = trainer.train_step(*pool[0])  # builds / captures the graph
     launches_capture = _lib.load().b200scn_launch_count() - launches0

@@ -1,0 +1,76 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: event sharding as the
+reference's IO does it, and the one-flat-buffer SUM all-reduce reproducing the reference's
+DataParallel gradient semantics (sum over replicas, BatchNorm statistics per replica)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from conftest import small_flags
+    from helpers import event_blob
+    from oracle.model import OracleUResNet, segmentation_loss
+    from uresnet_pytorch_b200.trainer import allreduce_sum_, shard_events
+
+    flags = small_flags(SPATIAL_SIZE=16, URESNET_FILTERS=4, URESNET_NUM_STRIDES=2)
+    torch.manual_seed(0)
+    net = OracleUResNet(flags).train()
+    for t in list(net.parameters()) + list(net.buffers()):
+        dist.broadcast(t.data, 0)
+    # 4 events per step, 2 per rank, contiguous blocks
+    data, label = event_blob(4, 16, seed=21)
+    mine = shard_events(4, world, rank)
+    sel = np.isin(data[:, -2].astype(int), mine)
+    d, l = torch.from_numpy(data[sel]), torch.from_numpy(label[sel])
+    loss, _ = segmentation_loss(net(d)[0], d, l)
+    loss.backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    grads = [p.grad for p in net.parameters()]
+    allreduce_sum_(grads)
+    torch.save({"local": local, "summed": [g.clone() for g in grads], "events": mine},
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sum_allreduce(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    assert r0["events"] == [0, 1] and r1["events"] == [2, 3]
+    for a, b, s0, s1 in zip(r0["local"], r1["local"], r0["summed"], r1["summed"]):
+        assert torch.equal(s0, s1)                       # every rank holds the same reduced gradient
+        assert torch.allclose(s0, a + b, rtol=0, atol=0)  # SUM, not mean
+    assert any((a - b).abs().max() > 0 for a, b in zip(r0["local"], r1["local"]))  # shards really differ
+
+
+def test_shard_events_matches_reference_assignment():
+    from uresnet_pytorch_b200.trainer import shard_events
+    # new_id = data_id // batch_per_gpu  (iotools_sparse.py:140)
+    for world, n in [(2, 8), (4, 8), (8, 64)]:
+        per = n // world
+        for r in range(world):
+            assert shard_events(n, world, r) == [i for i in range(n) if i // per == r]
+    with pytest.raises(ValueError):
+        shard_events(7, 2, 0)

@@ -13,6 +13,8 @@
 namespace b200scn {
 namespace {
 
+constexpr int kRowsPerBlock = 128;
+
 struct Layout {
   int threads, RL, blocks;
 };
@@ -21,7 +23,7 @@ Layout make_layout(int64_t n_cap, int C) {
   Layout L;
   L.RL = C >= 256 ? 1 : 256 / C;
   L.threads = C * L.RL;
-  int64_t b = cdiv(n_cap, 128);
+  int64_t b = cdiv(n_cap, kRowsPerBlock);
   const int64_t cap = (int64_t)sm_count() * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -48,7 +50,11 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
-  const int rpb = (n + gridDim.x - 1) / gridDim.x;
+  // only as many CTAs as the live row count warrants take part (static regime: the grid is
+  // sized for the capacity); the others leave before touching the ticket
+  const int nblk = max(1, min((int)gridDim.x, (n + kRowsPerBlock - 1) / kRowsPerBlock));
+  if ((int)blockIdx.x >= nblk) return;
+  const int rpb = (n + nblk - 1) / nblk;
   const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
 
   float cnt = 0.f, s1 = 0.f, s2 = 0.f, shift = 0.f;
@@ -80,17 +86,26 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
   __syncthreads();
   if (t == 0) {
     const unsigned ticket = atomicAdd(counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
+    is_last = (ticket == (unsigned)nblk - 1u);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (rl == 0) {
+  // fold the per-CTA partials: row lane rl takes CTAs rl, rl+RL, ...; lanes merged in order
+  {
     float N = 0.f, M = 0.f, S = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) {
-      const volatile float* p = part + (int64_t)b * 3 * C;
-      chan_merge(N, M, S, p[c], p[C + c], p[2 * C + c]);
+    for (int b = rl; b < nblk; b += RL) {
+      const float* p = part + (int64_t)b * 3 * C;
+      chan_merge(N, M, S, __ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c));
     }
+    sm[t] = N;
+    sm[T + t] = M;
+    sm[2 * T + t] = S;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    float N = sm[c], M = sm[T + c], S = sm[2 * T + c];
+    for (int j = 1; j < RL; ++j) chan_merge(N, M, S, sm[j * C + c], sm[T + j * C + c], sm[2 * T + j * C + c]);
     const float var_b = N > 0.f ? S / N : 0.f;
     save_mean[c] = M;
     save_invstd[c] = rsqrtf(var_b + eps);
@@ -133,7 +148,9 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
-  const int rpb = (n + gridDim.x - 1) / gridDim.x;
+  const int nblk = max(1, min((int)gridDim.x, (n + kRowsPerBlock - 1) / kRowsPerBlock));
+  if ((int)blockIdx.x >= nblk) return;
+  const int rpb = (n + nblk - 1) / nblk;
   const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
   const float mu = mean[c], is = invstd[c];
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -163,17 +180,27 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
   __syncthreads();
   if (t == 0) {
     const unsigned ticket = atomicAdd(counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
+    is_last = (ticket == (unsigned)nblk - 1u);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (rl == 0) {
+  {
     float a1 = 0.f, a2 = 0.f;
-    for (int bk = 0; bk < (int)gridDim.x; ++bk) {
-      const volatile float* p = part + (int64_t)bk * 2 * C;
-      a1 += p[c];
-      a2 += p[C + c];
+    for (int bk = rl; bk < nblk; bk += RL) {
+      const float* p = part + (int64_t)bk * 2 * C;
+      a1 += __ldcg(p + c);
+      a2 += __ldcg(p + C + c);
+    }
+    sm[t] = a1;
+    sm[T + t] = a2;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    float a1 = sm[c], a2 = sm[T + c];
+    for (int j = 1; j < RL; ++j) {
+      a1 += sm[j * C + c];
+      a2 += sm[T + j * C + c];
     }
     dbeta[c] = a1;
     dgamma[c] = a2;

@@ -88,17 +88,27 @@ __global__ void __launch_bounds__(MT >= 3 ? 256 : 512) k_conv_mma(const MmaParam
   float4* ring = reinterpret_cast<float4*>(warp_base + warp * per_warp + idx_bytes + mask_bytes);
 
   // ---- weights of this output-channel tile -> shared memory, mma A-fragment order ----------
-  for (int e = tid; e < w_elems; e += blockDim.x) {
-    const int r = e & 3, ln = (e >> 2) & 31;
-    int rest = e >> 7;
-    const int mt = rest % MT; rest /= MT;
-    const int s = rest % KS;
-    const int k = rest / KS;
-    const int gg = ln >> 2, tt = ln & 3;
-    const int ci = ((s >> 1) << 4) + 4 * tt + 2 * (s & 1) + (r >> 1);
-    const int co = cob + mt * 16 + gg + 8 * (r & 1);
-    const int kk = p.kflip ? (K - 1 - k) : k;
-    Wsm[e] = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)co * p.w_so);
+  // Global reads run along whichever of (ci, co) is contiguous (forward: co, dgrad: ci) so
+  // that a warp reads whole 128 B lines; the scatter into fragment order happens in smem.
+  {
+    const int CT = MT * 16;
+    const bool co_fast = (p.w_so == 1);
+    const int fast_n = co_fast ? CT : Cin, slow_n = co_fast ? Cin : CT;
+    const int total = K * slow_n * fast_n;
+    for (int e = tid; e < total; e += blockDim.x) {
+      const int f = e % fast_n;
+      int rest = e / fast_n;
+      const int sl = rest % slow_n;
+      const int k = rest / slow_n;
+      const int ci = co_fast ? sl : f, col = co_fast ? f : sl;  // col = output channel within this pass
+      const int kk = p.kflip ? (K - 1 - k) : k;
+      const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
+      const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
+      const int s = ((ci >> 4) << 1) + (rem >> 1);
+      const int mt = col >> 4, c = col & 15, gg = c & 7;
+      const int r = ((rem & 1) << 1) | (c >> 3);
+      Wsm[((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r] = v;
+    }
   }
   __syncthreads();
 
@@ -259,7 +269,17 @@ struct Plan {
   bool ok;
 };
 
-Plan make_plan(int K, int Cin, int Cout) {
+Plan make_plan_chunk(int K, int Cin, int Cout);
+
+// Largest input-channel chunk (multiple of 16) whose weights + ring fit; the layer is then
+// computed as a sum over chunks (later chunks accumulate into `out`).
+int pick_cin_chunk(int K, int Cin, int Cout) {
+  for (int c = Cin; c >= 16; c -= 16)
+    if (make_plan_chunk(K, c, Cout).ok) return c;
+  return 0;
+}
+
+Plan make_plan_chunk(int K, int Cin, int Cout) {
   Plan best{0, 0, 0, 0, false};
   const size_t per_warp = (size_t)K * 32 * 4 + 128 + (size_t)kStages * kNT * (Cin / 16) * 32 * 16;
   for (int mt = 4; mt >= 1; --mt) {
@@ -313,7 +333,7 @@ bool conv_mma_supported(int Cin, int Cout, int K, int64_t ldi, const void* in) {
   if (Cin % 16 != 0 || Cout % 16 != 0) return false;
   if (!(K == 1 || K == 4 || K == 8 || K == 9 || K == 27)) return false;
   if (ldi % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0) return false;
-  return make_plan(K, Cin, Cout).ok;
+  return pick_cin_chunk(K, Cin, Cout) > 0;
 }
 
 int conv_rows_mma(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so, int kflip,
@@ -321,24 +341,31 @@ int conv_rows_mma(const float* in, int64_t ldi, const float* W, int64_t w_sk, in
                   const int32_t* n_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate, int math_mode,
                   cudaStream_t st) {
   if (n_cap == 0) return 0;
-  Plan plan = make_plan(K, Cin, Cout);
-  if (!plan.ok) {
+  const int chunk = pick_cin_chunk(K, Cin, Cout);
+  if (chunk == 0) {
     set_error("conv_mma: shape not supported (Cin=%d Cout=%d K=%d)", Cin, Cout, K);
     return B200SCN_ERR_UNSUPPORTED;
   }
-  MmaParams p;
-  p.in = in; p.ldi = ldi; p.W = W; p.w_sk = w_sk; p.w_si = w_si; p.w_so = w_so; p.kflip = kflip;
-  p.table = table; p.ld = ld; p.parent = parent; p.kofs = kofs; p.n_cap = n_cap; p.n_dev = n_dev;
-  p.Cin = Cin; p.Cout = Cout; p.out = out; p.ldo = ldo; p.accumulate = accumulate;
-  p.x3 = (math_mode == B200SCN_MATH_TF32X3) ? 1 : 0;
-  p.warps = plan.warps;
-  switch (K) {
-    case 1: return launch_k<1>(p, plan, st);
-    case 4: return launch_k<4>(p, plan, st);
-    case 8: return launch_k<8>(p, plan, st);
-    case 9: return launch_k<9>(p, plan, st);
-    default: return launch_k<27>(p, plan, st);
+  for (int c0 = 0; c0 < Cin; c0 += chunk) {
+    const int cc = Cin - c0 < chunk ? Cin - c0 : chunk;
+    Plan plan = make_plan_chunk(K, cc, Cout);
+    MmaParams p;
+    p.in = in + c0; p.ldi = ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = w_sk; p.w_si = w_si; p.w_so = w_so;
+    p.kflip = kflip; p.table = table; p.ld = ld; p.parent = parent; p.kofs = kofs; p.n_cap = n_cap; p.n_dev = n_dev;
+    p.Cin = cc; p.Cout = Cout; p.out = out; p.ldo = ldo; p.accumulate = (c0 > 0) ? 1 : accumulate;
+    p.x3 = (math_mode == B200SCN_MATH_TF32X3) ? 1 : 0;
+    p.warps = plan.warps;
+    int rc;
+    switch (K) {
+      case 1: rc = launch_k<1>(p, plan, st); break;
+      case 4: rc = launch_k<4>(p, plan, st); break;
+      case 8: rc = launch_k<8>(p, plan, st); break;
+      case 9: rc = launch_k<9>(p, plan, st); break;
+      default: rc = launch_k<27>(p, plan, st); break;
+    }
+    if (rc) return rc;
   }
+  return 0;
 }
 
 }  // namespace b200scn

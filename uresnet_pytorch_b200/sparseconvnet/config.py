@@ -8,6 +8,11 @@ math_mode = MATH_FP32
 # False: eager regime (exact row counts, one host read-back per level).
 # True : static regime (capacity-sized matrices, device-side row counts, CUDA-graph capturable).
 static_shapes = False
+# True: weight-gradient kernels run on a side stream, overlapping the dgrad chain (forked and
+# joined with events, so it is capturable); callers must call functional.join_side_streams()
+# before consuming parameter gradients.
+overlap_wgrad = False
+
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None
 

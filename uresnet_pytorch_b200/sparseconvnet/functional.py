@@ -28,15 +28,49 @@ def _check_cuda_f32(*ts):
             raise RuntimeError("b200 sparseconvnet: features and weights are float32 (got %s)" % t.dtype)
 
 
+_side_streams = {}
+_side_dirty = set()
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def join_side_streams():
+    """Make the current stream wait for every weight-gradient kernel issued on a side stream."""
+    for key in list(_side_dirty):
+        torch.cuda.current_stream(torch.device(*key)).wait_stream(_side_streams[key])
+    _side_dirty.clear()
+
+
 def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
     Ca, Cb = A.shape[1], B.shape[1]
     L = _lib.load()
     nbytes = L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
-    dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
-    _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
-              table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0, math,
-              scratch.data_ptr(), nbytes, _stream())
+
+    def run():
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+        dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
+        _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
+                  table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0,
+                  math, scratch.data_ptr(), nbytes, _stream())
+        return dW
+
+    if not config.overlap_wgrad:
+        return run()
+    main = torch.cuda.current_stream(A.device)
+    side = _side_stream(A.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dW = run()
+    # inputs were allocated on the main stream but are read on the side stream
+    A.record_stream(side)
+    B.record_stream(side)
+    dW.record_stream(main)
+    _side_dirty.add((A.device.type, A.device.index))
     return dW
 
 

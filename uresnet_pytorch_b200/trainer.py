@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import sparseconvnet as scn
+from .sparseconvnet import functional as scn_functional
 from .model import SegmentationLoss, UResNet
 
 
@@ -29,14 +30,37 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized()) else None
 
 
+def allreduce_sum_(tensors):
+    """In-place SUM all-reduce of a list of dense tensors through ONE flat buffer (one collective
+    per step).  SUM, not mean: the reference's DataParallel reduce-adds replica gradients
+    (R/uresnet/ops.py:8 -> Broadcast.backward) and divides only by the number of accumulated
+    forwards (R/uresnet/trainval.py:23-25).  No-op without an initialised process group."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1 or not tensors:
+        return
+    flat = torch._utils._flatten_dense_tensors(tensors)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    torch._foreach_copy_(tensors, list(torch._utils._unflatten_dense_tensors(flat, tensors)))
+
+
+def shard_events(n_events, world, rank):
+    """Contiguous block of events owned by `rank`, as the reference's IO assigns them:
+    new_id = data_id // batch_per_gpu (R/uresnet/iotools/iotools_sparse.py:140)."""
+    if n_events % world != 0:
+        raise ValueError("BATCH_SIZE must be a multiple of the number of GPUs (R/uresnet/flags.py:176-183)")
+    per = n_events // world
+    return list(range(rank * per, (rank + 1) * per))
+
+
 class Trainer(object):
     def __init__(self, flags, lr=1e-3, graph=False, capacity=None, events_per_step=1, train=True, device=None,
-                 math_mode=None, seed=0):
+                 math_mode=None, seed=0, overlap_wgrad=True):
         self.flags = flags
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.graph_mode = graph
         self.train = train
         self.events_per_step = events_per_step
+        self.overlap_wgrad = overlap_wgrad
         self.math_mode = scn.config.math_mode if math_mode is None else math_mode
         torch.manual_seed(seed)
         self.net = UResNet(flags).to(self.device)
@@ -51,7 +75,7 @@ class Trainer(object):
         self.n_params = sum(p.numel() for p in self.params)
         self.opt = None
         if train:
-            self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, foreach=True)
+            self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, fused=True)
         self.ncol = flags.DATA_DIM + 2
         self._graph = None
         self._cap = 0
@@ -75,13 +99,7 @@ class Trainer(object):
         self._graph = None
 
     def _allreduce_grads(self):
-        dist = _dist()
-        if dist is None or dist.get_world_size() == 1:
-            return
-        grads = [p.grad for p in self.params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
+        allreduce_sum_([p.grad for p in self.params if p.grad is not None])
 
     def _fwd_bwd(self, data, label, valid=None):
         """One forward (+ backward + optimiser step when training) on device tensors."""
@@ -96,7 +114,13 @@ class Trainer(object):
                     loss, acc = self.criterion([logits], [data], [label], None)
                 if self.train:
                     self.opt.zero_grad(set_to_none=True)
-                    loss.backward()
+                    prev = scn.config.overlap_wgrad
+                    scn.config.overlap_wgrad = self.overlap_wgrad
+                    try:
+                        loss.backward()
+                    finally:
+                        scn.config.overlap_wgrad = prev
+                        scn_functional.join_side_streams()
                     self._allreduce_grads()
                     self.opt.step()
         return loss, acc, logits
