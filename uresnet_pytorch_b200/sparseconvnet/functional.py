@@ -30,6 +30,7 @@ def _check_cuda_f32(*ts):
 
 _side_streams = {}
 _side_dirty = set()
+_side_keepalive = []  # buffers a side-stream kernel still reads/writes; released at the join
 
 
 def _side_stream(device):
@@ -44,6 +45,8 @@ def join_side_streams():
     for key in list(_side_dirty):
         torch.cuda.current_stream(torch.device(*key)).wait_stream(_side_streams[key])
     _side_dirty.clear()
+    # frees happen on the main stream *after* it waited for the side stream: stream-ordered reuse is safe
+    del _side_keepalive[:]
 
 
 def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
@@ -51,25 +54,24 @@ def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
     L = _lib.load()
     nbytes = L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
 
+    # every buffer is allocated on the main stream; only the kernels move to the side stream
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
+
     def run():
-        scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
-        dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
         _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
                   table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0,
                   math, scratch.data_ptr(), nbytes, _stream())
-        return dW
 
     if not config.overlap_wgrad:
-        return run()
+        run()
+        return dW
     main = torch.cuda.current_stream(A.device)
     side = _side_stream(A.device)
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        dW = run()
-    # inputs were allocated on the main stream but are read on the side stream
-    A.record_stream(side)
-    B.record_stream(side)
-    dW.record_stream(main)
+        run()
+    _side_keepalive.append((scratch, A, B, table))
     _side_dirty.add((A.device.type, A.device.index))
     return dW
 
