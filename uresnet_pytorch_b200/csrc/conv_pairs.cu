@@ -1,0 +1,428 @@
+// Gather-GEMM sparse convolution, "dense pairs" formulation (forward / dgrad of
+// SubmanifoldConvolution, Convolution, Deconvolution, NetworkInNetwork) on the tensor pipe.
+//
+// conv_mma.cu keeps output rows in registers and pays an MMA for every (offset, 8-site tile)
+// that has at least one neighbour -- at the fine U-Net levels only ~2.4 of the 8 columns of
+// such an MMA carry data and the bookkeeping around it dominates the issue slots (ncu:
+// profiles/README.md).  Here each warp owns R = 32*NCH consecutive output rows and, for every
+// kernel offset k in order,
+//   1. compacts the valid (input row, local output row) rule pairs of its rows from the
+//      offset-major table with ballot + popc (deterministic, row order),
+//   2. gathers the input rows of 8 pairs at a time straight into registers (one LDG.128 per
+//      lane per 16 channels; a lane's registers are exactly its mma B fragment),
+//   3. multiplies the dense 8-pair tile with W_k on mma.sync.m16n8k8 (tf32, optional 3-term
+//      split for fp32-equivalent accuracy), and
+//   4. adds the result into a per-warp shared-memory accumulator [R][Cout tile] -- plain
+//      read-modify-write, because within one offset every output row appears at most once
+//       and offsets are processed in order by the same warp.
+// The accumulator is written to HBM once, coalesced.  Gathers of offset k+1 are issued before
+// the MMAs of offset k (register ping-pong); table entries are prefetched three offsets ahead.
+// Weights come either from shared memory (fragment order, pre-split hi/lo; large inputs) or
+// straight from L1/L2 (small inputs, where a per-CTA weight fill would dominate).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b200scn {
+namespace {
+
+constexpr int kMaxSmem = 220 * 1024;
+
+struct PairParams {
+  const float* in; int64_t ldi;
+  const float* W; int64_t w_sk, w_si, w_so; int kflip;
+  const int32_t* table; int64_t ld;
+  const int32_t* parent; const uint8_t* kofs;
+  int K;
+  int64_t n_cap; const int32_t* n_dev;
+  float* out; int64_t ldo; int accumulate; int x3;
+  int warps;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Q = Cin/16, MT = Cout tile/16, NCH = 32-row chunks per warp, WSMEM = weights in smem
+template <int Q, int MT, int NCH, bool WSMEM>
+__global__ void __launch_bounds__(NCH == 2 ? 512 : 128) k_conv_pairs(const PairParams p) {
+  constexpr int R = 32 * NCH, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
+  constexpr int kQM = Q > MT ? Q : MT;
+  constexpr int GB = kQM == 1 ? 4 : (kQM == 2 ? 2 : 1);  // 8-pair groups whose gathers are in flight together
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = live_rows(p.n_dev, p.n_cap);
+  const int warps = p.warps;
+  if ((int64_t)blockIdx.x * warps * R >= n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = p.K;
+  const int cob = blockIdx.y * CT;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // ---- shared memory carve-up ----------------------------------------------------------------
+  const int w_elems = WSMEM ? K * KS * MT * 128 : 0;
+  float* Whi = reinterpret_cast<float*>(smem_raw);
+  float* Wlo = Whi + w_elems;  // only filled / read when p.x3
+  unsigned char* wbase = smem_raw + (size_t)w_elems * 4 * (p.x3 ? 2 : 1);
+  constexpr size_t kAccBytes = (size_t)R * AS * 4;
+  constexpr size_t kListBytes = (size_t)2 * R * 4 + (size_t)2 * R;  // in_s int32[2][R] + out_s uint8[2][R]
+  constexpr size_t kPerWarp = (kAccBytes + kListBytes + 15) & ~(size_t)15;
+  float* acc = reinterpret_cast<float*>(wbase + (size_t)warp * kPerWarp);
+  int32_t* in_s = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(acc) + kAccBytes);
+  uint8_t* out_s = reinterpret_cast<uint8_t*>(in_s + 2 * R);
+
+  if (WSMEM) {
+    // coalesced read along the contiguous weight dimension, scatter into A-fragment order
+    const bool co_fast = (p.w_so == 1);
+    const int fast_n = co_fast ? CT : 16 * Q, slow_n = co_fast ? 16 * Q : CT;
+    const int total = K * slow_n * fast_n;
+    for (int e = tid; e < total; e += blockDim.x) {
+      const int f = e % fast_n;
+      int rest = e / fast_n;
+      const int sl = rest % slow_n;
+      const int k = rest / slow_n;
+      const int ci = co_fast ? sl : f, col = co_fast ? f : sl;
+      const int kk = p.kflip ? (K - 1 - k) : k;
+      const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
+      const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
+      const int s = ((ci >> 4) << 1) + (rem >> 1);
+      const int mt = col >> 4, c = col & 15, gg = c & 7;
+      const int r = ((rem & 1) << 1) | (c >> 3);
+      const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r;
+      const float hi = __uint_as_float(to_tf32(v));
+      Whi[dst] = hi;
+      if (p.x3) Wlo[dst] = v - hi;
+    }
+    __syncthreads();
+  }
+
+  const int64_t n_tiles = ((int64_t)n + R - 1) / R;
+  for (int64_t wt = (int64_t)blockIdx.x * warps + warp; wt < n_tiles; wt += (int64_t)gridDim.x * warps) {
+    const int base = (int)(wt * R);
+    __syncwarp();
+    for (int e = lane; e < R * AS / 4; e += 32) reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- rule-table entries of this warp's rows -------------------------------------------
+    int pk[NCH], pp[NCH];
+    if (p.parent != nullptr) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int row = base + 32 * c + lane;
+        pk[c] = -1; pp[c] = -1;
+        if (row < n) { pk[c] = p.kofs[row]; pp[c] = __ldg(p.parent + row); }
+      }
+    }
+    auto load_tbl = [&](int k, int (&dst)[NCH]) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int row = base + 32 * c + lane;
+        int e = -1;
+        if (k < K && row < n) {
+          if (p.parent != nullptr) e = (pk[c] == k) ? pp[c] : -1;
+          else if (p.table != nullptr) e = __ldg(p.table + (int64_t)k * p.ld + row);
+          else e = row;
+        }
+        dst[c] = e;
+      }
+    };
+    auto compact = [&](const int (&src)[NCH], int buf) -> int {
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t m = __ballot_sync(0xffffffffu, src[c] >= 0);
+        if (src[c] >= 0) {
+          const int pos = cnt + __popc(m & lt_mask);
+          in_s[buf * R + pos] = src[c];
+          out_s[buf * R + pos] = (uint8_t)(32 * c + lane);
+        }
+        cnt += __popc(m);
+      }
+      __syncwarp();
+      return cnt;
+    };
+    auto gather = [&](int buf, int cnt, int gb0, float4 (&G)[GB][Q]) {
+#pragma unroll
+      for (int gi = 0; gi < GB; ++gi) {
+        const int pi = 8 * (gb0 + gi) + g;
+        const int idx = pi < cnt ? in_s[buf * R + pi] : -1;
+        const float* src = p.in + (int64_t)(idx >= 0 ? idx : 0) * p.ldi + 4 * t;
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          G[gi][q] = idx >= 0 ? ldg_f4(src + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto compute = [&](int kk, float4 (&G)[GB][Q], int buf, int cnt) {
+      for (int gb0 = 0; 8 * gb0 < cnt; gb0 += GB) {
+        if (gb0 > 0) gather(buf, cnt, gb0, G);
+        const int ngr = min(GB, (cnt - 8 * gb0 + 7) >> 3);
+        float d[GB][MT][4];
+#pragma unroll
+        for (int gi = 0; gi < GB; ++gi)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) d[gi][mt][r] = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int s = 2 * q + h;
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (WSMEM) {
+                const int off = (((kk * KS + s) * MT + mt) * 32 + lane) * 4;
+                const float4 a4 = *reinterpret_cast<const float4*>(Whi + off);
+                ah[mt][0] = __float_as_uint(a4.x); ah[mt][1] = __float_as_uint(a4.y);
+                ah[mt][2] = __float_as_uint(a4.z); ah[mt][3] = __float_as_uint(a4.w);
+                if (p.x3) {
+                  const float4 l4 = *reinterpret_cast<const float4*>(Wlo + off);
+                  al[mt][0] = __float_as_uint(l4.x); al[mt][1] = __float_as_uint(l4.y);
+                  al[mt][2] = __float_as_uint(l4.z); al[mt][3] = __float_as_uint(l4.w);
+                }
+              } else {
+                const int kw = p.kflip ? (K - 1 - kk) : kk;
+                const float* wp = p.W + (int64_t)kw * p.w_sk + (int64_t)(16 * q + 4 * t + 2 * h) * p.w_si +
+                                  (int64_t)(cob + 16 * mt + g) * p.w_so;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float v = __ldg(wp + (int64_t)(r >> 1) * p.w_si + (int64_t)(8 * (r & 1)) * p.w_so);
+                  ah[mt][r] = to_tf32(v);
+                  al[mt][r] = __float_as_uint(v - __uint_as_float(ah[mt][r]));
+                }
+              }
+            }
+#pragma unroll
+            for (int gi = 0; gi < GB; ++gi) {
+              if (gi < ngr) {
+                const float bx = h ? G[gi][q].z : G[gi][q].x;
+                const float by = h ? G[gi][q].w : G[gi][q].y;
+                const uint32_t b0 = to_tf32(bx), b1 = to_tf32(by);
+                if (p.x3) {
+                  const uint32_t l0 = __float_as_uint(bx - __uint_as_float(b0));
+                  const uint32_t l1 = __float_as_uint(by - __uint_as_float(b1));
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    mma_tf32(d[gi][mt], al[mt], b0, b1);
+                    mma_tf32(d[gi][mt], ah[mt], l0, l1);
+                  }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(d[gi][mt], ah[mt], b0, b1);
+              }
+            }
+          }
+        }
+        // accumulate D^T fragments into the warp's output rows
+#pragma unroll
+        for (int gi = 0; gi < GB; ++gi) {
+          if (gi < ngr) {
+            const int p0 = 8 * (gb0 + gi) + 2 * t;
+            const int o0 = p0 < cnt ? out_s[buf * R + p0] : -1;
+            const int o1 = p0 + 1 < cnt ? out_s[buf * R + p0 + 1] : -1;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (o0 >= 0) {
+                acc[o0 * AS + 16 * mt + g] += d[gi][mt][0];
+                acc[o0 * AS + 16 * mt + g + 8] += d[gi][mt][2];
+              }
+              if (o1 >= 0) {
+                acc[o1 * AS + 16 * mt + g] += d[gi][mt][1];
+                acc[o1 * AS + 16 * mt + g + 8] += d[gi][mt][3];
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    };
+
+    // ---- software pipeline over the offsets ----------------------------------------------------
+    int T0[NCH], T1[NCH], T2[NCH];
+    float4 G0[GB][Q], G1[GB][Q];
+    int cnt0 = 0, cnt1 = 0;
+    {
+      int Tc[NCH];
+      load_tbl(0, Tc);
+      load_tbl(1, T0);
+      load_tbl(2, T1);
+      load_tbl(3, T2);
+      cnt0 = compact(Tc, 0);
+      gather(0, cnt0, 0, G0);
+    }
+    for (int k = 0; k < K; k += 2) {
+      if (k + 1 < K) {
+        cnt1 = compact(T0, 1);
+        gather(1, cnt1, 0, G1);
+      }
+      compute(k, G0, 0, cnt0);
+      if (k + 1 >= K) break;
+      // T1 holds table[k+2], T2 holds table[k+3]; refill T0 with table[k+4]
+      if (k + 2 < K) {
+        cnt0 = compact(T1, 0);
+        gather(0, cnt0, 0, G0);
+      }
+      compute(k + 1, G1, 1, cnt1);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) T0[c] = T2[c];
+      load_tbl(k + 4, T1);
+      load_tbl(k + 5, T2);
+    }
+
+    // ---- epilogue: accumulator -> out, coalesced ---------------------------------------------------
+    __syncwarp();
+    const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    for (int e = lane; e < R * (CT / 4); e += 32) {
+      const int row = e / (CT / 4), c4 = e - row * (CT / 4);
+      if (base + row < n) {
+        float4 v = *reinterpret_cast<const float4*>(acc + row * AS + 4 * c4);
+        float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
+        if (vec_ok) {
+          if (p.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(o);
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o) = v;
+        } else {
+          if (p.accumulate) { v.x += o[0]; v.y += o[1]; v.z += o[2]; v.w += o[3]; }
+          o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+      }
+    }
+  }
+}
+
+struct PPlan {
+  int Q, MT, NCH, passes, warps, ctas_per_sm;
+  bool wsmem, ok;
+  size_t smem;
+};
+
+size_t per_warp_bytes(int MT, int NCH) {
+  const int R = 32 * NCH, AS = 16 * MT + 8;
+  size_t b = (size_t)R * AS * 4 + (size_t)2 * R * 4 + (size_t)2 * R;
+  return (b + 15) & ~(size_t)15;
+}
+
+// Cin here is already a chunk (<= 64, multiple of 16)
+PPlan plan_pairs(int K, int Cin, int Cout, int64_t n_cap, int x3) {
+  PPlan pl{};
+  pl.ok = false;
+  if (Cin % 16 || Cout % 16 || Cin > 64 || Cin < 16) return pl;
+  pl.Q = Cin / 16;
+  const int cot = Cout / 16;
+  pl.MT = cot % 4 == 0 ? 4 : (cot % 3 == 0 ? 3 : (cot % 2 == 0 ? 2 : 1));
+  const bool large = n_cap >= 65536;
+  pl.NCH = large ? 2 : 1;
+  if (!large && pl.MT > 2) pl.MT = (cot % 2 == 0) ? 2 : 1;  // more, smaller tasks when rows are few
+  pl.passes = cot / pl.MT;
+  const size_t pw = per_warp_bytes(pl.MT, pl.NCH);
+  const size_t wbytes = (size_t)K * Cin * 16 * pl.MT * 4 * (x3 ? 2 : 1);
+  pl.wsmem = large && (wbytes + 8 * pw <= (size_t)kMaxSmem);
+  const size_t fixed = pl.wsmem ? wbytes : 0;
+  int warps = large ? 16 : 4;
+  while (warps > 2 && fixed + warps * pw > (size_t)kMaxSmem) warps >>= 1;
+  if (fixed + warps * pw > (size_t)kMaxSmem) return pl;
+  pl.warps = warps;
+  pl.smem = fixed + warps * pw;
+  int cps = (int)((size_t)(227 * 1024) / (pl.smem + 1024));
+  const int by_threads = 2048 / (warps * 32);
+  if (cps > by_threads) cps = by_threads;
+  if (cps > 8) cps = 8;
+  if (cps < 1) cps = 1;
+  pl.ctas_per_sm = cps;
+  pl.ok = true;
+  return pl;
+}
+
+template <int Q, int MT, int NCH, bool WSMEM>
+int launch_pairs(const PairParams& p, const PPlan& pl, cudaStream_t st) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(k_conv_pairs<Q, MT, NCH, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kMaxSmem));
+    configured = true;
+  }
+  const int R = 32 * NCH;
+  const int64_t tiles = cdiv(p.n_cap, R);
+  int64_t gx = cdiv(tiles, pl.warps);
+  int64_t gmax = ((int64_t)sm_count() * pl.ctas_per_sm) / pl.passes;
+  if (!WSMEM) gmax = (int64_t)sm_count() * pl.ctas_per_sm;  // no per-CTA prologue: no reason to hold CTAs back
+  if (gmax < 1) gmax = 1;
+  if (gx > gmax) gx = gmax;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)pl.passes);
+  k_conv_pairs<Q, MT, NCH, WSMEM><<<grid, pl.warps * 32, pl.smem, st>>>(p);
+  count_launches(1);
+  B200_CHECK_LAUNCH("conv_pairs");
+  return 0;
+}
+
+template <int Q, int MT>
+int launch_qm(const PairParams& p, const PPlan& pl, cudaStream_t st) {
+  if (pl.NCH == 2) {
+    if (pl.wsmem) return launch_pairs<Q, MT, 2, true>(p, pl, st);
+    return launch_pairs<Q, MT, 2, false>(p, pl, st);
+  }
+  return launch_pairs<Q, MT, 1, false>(p, pl, st);
+}
+
+template <int Q>
+int launch_q(const PairParams& p, const PPlan& pl, cudaStream_t st) {
+  switch (pl.MT) {
+    case 1: return launch_qm<Q, 1>(p, pl, st);
+    case 2: return launch_qm<Q, 2>(p, pl, st);
+    case 3: return launch_qm<Q, 3>(p, pl, st);
+    default: return launch_qm<Q, 4>(p, pl, st);
+  }
+}
+
+}  // namespace
+
+bool conv_pairs_supported(int Cin, int Cout, int K, int64_t ldi, const void* in) {
+  if (Cin % 16 != 0 || Cout % 16 != 0 || K < 1 || K > 64) return false;
+  if (ldi % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0) return false;
+  return true;
+}
+
+int conv_rows_pairs(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so, int kflip,
+                    const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs, int K, int64_t n_cap,
+                    const int32_t* n_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate, int math_mode,
+                    cudaStream_t st) {
+  if (n_cap == 0) return 0;
+  const int x3 = (math_mode == B200SCN_MATH_TF32X3) ? 1 : 0;
+  // input channels in chunks of <= 64 (register budget of the gather ping-pong); later chunks accumulate
+  for (int c0 = 0; c0 < Cin; c0 += 64) {
+    const int cc = Cin - c0 < 64 ? Cin - c0 : 64;
+    PPlan pl = plan_pairs(K, cc, Cout, n_cap, x3);
+    if (!pl.ok) {
+      set_error("conv_pairs: shape not supported (Cin=%d Cout=%d K=%d)", Cin, Cout, K);
+      return B200SCN_ERR_UNSUPPORTED;
+    }
+    PairParams p;
+    p.in = in + c0; p.ldi = ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = w_sk; p.w_si = w_si; p.w_so = w_so;
+    p.kflip = kflip; p.table = table; p.ld = ld; p.parent = parent; p.kofs = kofs; p.K = K; p.n_cap = n_cap;
+    p.n_dev = n_dev; p.out = out; p.ldo = ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.x3 = x3;
+    p.warps = pl.warps;
+    int rc;
+    switch (pl.Q) {
+      case 1: rc = launch_q<1>(p, pl, st); break;
+      case 2: rc = launch_q<2>(p, pl, st); break;
+      case 3: rc = launch_q<3>(p, pl, st); break;
+      default: rc = launch_q<4>(p, pl, st); break;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace b200scn
