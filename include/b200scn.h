@@ -170,6 +170,29 @@ int b200scn_segsum_rows(const float* src, int64_t lds, const int32_t* first_idx,
 int b200scn_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n_cap,
                      const int32_t* n_dev, int C, float* out, int64_t ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (vi) dense path -- the Conv{2,3}d / ConvTranspose{2,3}d / replicate-pad family of
+ * /root/reference/uresnet/models/uresnet_dense.py:12-226 on channels-last [B, (D,) H, W, C] fp32.
+ * geom_host = int32[11] on the HOST: {mode, dims, in_z, in_y, in_x, out_z, out_y, out_x, k, stride, pad}
+ * (z sizes = 1 for 2D); mode 1: in = out*stride + tap - pad (nn.Conv forward, ConvTranspose dgrad),
+ * mode 2: in = (out + pad - tap)/stride (nn.ConvTranspose forward, Conv dgrad).  Tap index
+ * enumerates the k^dims box with the last dimension fastest; weights via element strides.
+ * ------------------------------------------------------------------------------------- */
+int b200scn_dense_conv(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
+                       const float* bias, const int32_t* geom_host, int batch, int Cin, int Cout, float* out,
+                       int64_t ldo, void* stream);
+int64_t b200scn_dense_wgrad_scratch_bytes(const int32_t* geom_host, int batch, int Ca, int Cb);
+/* dW[k][ca][cb] = sum_o A[idx(o,k)][ca] * B[o][cb] (gather_b == 0) or A[o][ca] * B[idx(o,k)][cb] (gather_b == 1) */
+int b200scn_dense_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* geom_host, int batch,
+                        int gather_b, int Ca, int Cb, float* dW, void* scratch, int64_t scratch_bytes, void* stream);
+/* F.pad(mode='replicate') on channels-last data and its backward; sizes are (z, y, x) host int32[3] */
+int b200scn_pad_replicate(const float* src, float* dst, int batch, int C, const int32_t* in_sz_host,
+                          const int32_t* pl_host, const int32_t* pr_host, int backward, void* stream);
+/* out[c] = sum_r x[r, c]  (bias gradients) */
+int64_t b200scn_colsum_scratch_bytes(int C);
+int b200scn_colsum(const float* x, int64_t ldx, int64_t n, int C, float* out, void* scratch, int64_t scratch_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""Dense path: hand-written CUDA Conv/ConvTranspose/pad/BatchNorm vs golden vectors produced by
+the reference's own uresnet_dense.py on torch-CPU (tests/golden/make_dense_golden.py), plus
+layer-level checks against torch.nn.functional on the GPU-side inputs copied to the CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import small_flags
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_dense_model_matches_reference_golden(dim):
+    from uresnet_pytorch_b200.dense import DenseUResNet
+    g = np.load(os.path.join(GOLDEN, "dense_tiny_%dd.npz" % dim))
+    flags = small_flags(DATA_DIM=dim, SPATIAL_SIZE=int(g["ss"]), URESNET_FILTERS=int(g["uf"]),
+                        URESNET_NUM_STRIDES=int(g["uns"]))
+    net = DenseUResNet(flags)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    assert list(net.state_dict().keys()) == list(sd.keys())      # reference checkpoints load unchanged
+    net.load_state_dict(sd)
+    net.cuda().train()
+    out = net(torch.from_numpy(g["x"]).cuda())
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    assert (out.detach().cpu() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    (out * torch.from_numpy(g["w"]).cuda()).sum().backward()
+    num = den = 0.0
+    for name, p in net.named_parameters():
+        key = "grad." + name
+        if key not in g.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name   # unused shortcut branches
+            continue
+        a, b = p.grad.detach().cpu().double(), torch.from_numpy(g[key]).double()
+        num += (a - b).pow(2).sum().item()
+        den += b.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 2e-3
+
+
+@pytest.mark.parametrize("dims,k,stride,cin,cout", [(3, 3, 1, 3, 5), (3, 3, 2, 4, 8), (3, 1, 2, 8, 4), (2, 3, 2, 5, 7),
+                                                    (3, 3, 1, 16, 32)])
+def test_dense_conv_layer_against_torch(dims, k, stride, cin, cout):
+    from uresnet_pytorch_b200.dense import Conv
+    torch.manual_seed(0)
+    size = 10
+    conv = Conv(dims, cin, cout, k, stride).cuda()
+    x = torch.randn((2, cin) + (size,) * dims)
+    xg = (x.permute(0, 2, 3, 4, 1) if dims == 3 else x.permute(0, 2, 3, 1).unsqueeze(1)).contiguous().cuda()
+    xg.requires_grad_(True)
+    y = conv(xg)
+    # torch reference: replicate pad (same rule) + padding-free convolution
+    xr = x.clone().requires_grad_(True)
+    rem = size % stride
+    tot = max(k - (stride if rem == 0 else rem), 0)
+    pad = (tot // 2, tot - tot // 2) * dims
+    fn = F.conv3d if dims == 3 else F.conv2d
+    yr = fn(F.pad(xr, pad, mode="replicate") if tot else xr, conv.weight.detach().cpu(), conv.bias.detach().cpu(),
+            stride=stride)
+    yg = y.squeeze(1).permute(0, 3, 1, 2) if dims == 2 else y.permute(0, 4, 1, 2, 3)
+    assert yg.shape == yr.shape
+    assert (yg.detach().cpu() - yr.detach()).abs().max().item() <= 2e-5 * yr.abs().max().item()
+    go = torch.randn_like(yr)
+    yr.backward(go)
+    yg.backward(go.cuda())
+    dxg = xg.grad.squeeze(1).permute(0, 3, 1, 2) if dims == 2 else xg.grad.permute(0, 4, 1, 2, 3)
+    assert rel_l2(dxg, xr.grad) <= 1e-4
+    # weight / bias gradients
+    wref = conv.weight.detach().cpu().requires_grad_(True)
+    bref = conv.bias.detach().cpu().requires_grad_(True)
+    fn(F.pad(x, pad, mode="replicate") if tot else x, wref, bref, stride=stride).mul(go).sum().backward()
+    assert rel_l2(conv.weight.grad, wref.grad) <= 1e-4
+    assert rel_l2(conv.bias.grad, bref.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("dims", [3, 2])
+def test_dense_conv_transpose_against_torch(dims):
+    from uresnet_pytorch_b200.dense import ConvTranspose
+    torch.manual_seed(1)
+    cin, cout, size = 6, 4, 5
+    up = ConvTranspose(dims, cin, cout).cuda()
+    x = torch.randn((2, cin) + (size,) * dims)
+    xg = (x.permute(0, 2, 3, 4, 1) if dims == 3 else x.permute(0, 2, 3, 1).unsqueeze(1)).contiguous().cuda()
+    xg.requires_grad_(True)
+    y = up(xg)
+    fn = F.conv_transpose3d if dims == 3 else F.conv_transpose2d
+    xr = x.clone().requires_grad_(True)
+    wref = up.weight.detach().cpu().requires_grad_(True)
+    bref = up.bias.detach().cpu().requires_grad_(True)
+    yr = fn(xr, wref, bref, stride=2, padding=1, output_padding=1)
+    yg = y.squeeze(1).permute(0, 3, 1, 2) if dims == 2 else y.permute(0, 4, 1, 2, 3)
+    assert yg.shape == yr.shape and yr.shape[-1] == 2 * size
+    assert (yg.detach().cpu() - yr.detach()).abs().max().item() <= 2e-5 * yr.abs().max().item()
+    go = torch.randn_like(yr)
+    yr.backward(go)
+    yg.backward(go.cuda())
+    dxg = xg.grad.squeeze(1).permute(0, 3, 1, 2) if dims == 2 else xg.grad.permute(0, 4, 1, 2, 3)
+    assert rel_l2(dxg, xr.grad) <= 1e-4
+    assert rel_l2(up.weight.grad, wref.grad) <= 1e-4
+    assert rel_l2(up.bias.grad, bref.grad) <= 1e-4
+
+
+def test_dense_batchnorm_matches_torch():
+    from uresnet_pytorch_b200.dense import BatchNorm
+    torch.manual_seed(2)
+    x = torch.randn(2, 4, 5, 6, 8)
+    bn = BatchNorm(8, relu=True).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.3, 0.3)
+    xg = x.cuda().requires_grad_(True)
+    y = bn(xg)
+    ref = torch.nn.BatchNorm3d(8, track_running_stats=False)
+    ref.weight.data.copy_(bn.weight.detach().cpu())
+    ref.bias.data.copy_(bn.bias.detach().cpu())
+    xr = x.permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    yr = F.relu(ref(xr))
+    assert (y.detach().cpu().permute(0, 4, 1, 2, 3) - yr.detach()).abs().max().item() <= 1e-5
+    go = torch.randn_like(yr)
+    yr.backward(go)
+    y.backward(go.permute(0, 2, 3, 4, 1).contiguous().cuda())
+    assert rel_l2(xg.grad.permute(0, 4, 1, 2, 3), xr.grad) <= 1e-4

@@ -40,7 +40,7 @@ int conv_parent_simt(const float*, int64_t, const float*, int64_t, int64_t, int6
                      int, int64_t, const int32_t*, int, int, float*, int64_t, cudaStream_t);
 int64_t wgrad_scratch_bytes_simt(int64_t, int, int, int);
 int wgrad_table_simt(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
-                     const int32_t*, int, int, float*, int, void*, int64_t, cudaStream_t);
+                     const int32_t*, int, int, float*, int, void*, int64_t, cudaStream_t, const DenseGeom&);
 // conv_mma.cu
 bool conv_mma_supported(int Cin, int Cout, int K, int64_t ldi, const void* in);
 int conv_rows_mma(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t,
@@ -137,5 +137,5 @@ extern "C" int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, 
     return wgrad_table_mma(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, math_mode,
                            scratch, scratch_bytes, (cudaStream_t)stream);
   return wgrad_table_simt(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, scratch,
-                          scratch_bytes, (cudaStream_t)stream);
+                          scratch_bytes, (cudaStream_t)stream, DenseGeom{});
 }

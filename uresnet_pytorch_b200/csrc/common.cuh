@@ -74,4 +74,41 @@ __device__ __forceinline__ int hash_find(const uint64_t* __restrict__ tkeys, con
   }
 }
 
+// Implicit rule "table" of a dense grid: maps (output voxel row, kernel tap) to the input voxel
+// row of a channels-last [B, (D,) H, W, C] tensor, or -1.  mode 1: strided correlation
+// (in = out * stride + tap - pad), mode 2: its transpose (in = (out + pad - tap) / stride).
+struct DenseGeom {
+  int mode, dims;
+  int in_sz[3], out_sz[3];  // (z, y, x); z = 1 for 2D
+  int ks, stride, pad;
+};
+
+__device__ __forceinline__ int dense_index(const DenseGeom& gm, int o, int k) {
+  int oc[3], kc[3];
+  oc[2] = o % gm.out_sz[2]; o /= gm.out_sz[2];
+  oc[1] = o % gm.out_sz[1]; o /= gm.out_sz[1];
+  oc[0] = o % gm.out_sz[0]; o /= gm.out_sz[0];
+  kc[2] = k % gm.ks; k /= gm.ks;
+  kc[1] = k % gm.ks; k /= gm.ks;
+  kc[0] = k;  // 0 for 2D
+  int lin = o;  // batch index
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int ic;
+    if (gm.dims == 2 && d == 0) {
+      ic = 0;
+    } else if (gm.mode == 1) {
+      ic = oc[d] * gm.stride + kc[d] - gm.pad;
+      if (ic < 0 || ic >= gm.in_sz[d]) return -1;
+    } else {
+      const int tnum = oc[d] + gm.pad - kc[d];
+      if (tnum < 0 || tnum % gm.stride != 0) return -1;
+      ic = tnum / gm.stride;
+      if (ic >= gm.in_sz[d]) return -1;
+    }
+    lin = lin * gm.in_sz[d] + ic;
+  }
+  return lin;
+}
+
 }  // namespace b200scn

@@ -25,7 +25,7 @@ k_conv_rows(const float* __restrict__ in, int64_t ldi, const float* __restrict__
             int64_t w_so, int kflip, const int32_t* __restrict__ table, int64_t ld,
             const int32_t* __restrict__ parent, const uint8_t* __restrict__ kofs, int K, int64_t n_cap,
             const int32_t* __restrict__ n_dev, int Cin, int Cout, float* __restrict__ out, int64_t ldo,
-            int accumulate) {
+            int accumulate, const DenseGeom geom, const float* __restrict__ bias) {
   __shared__ float in_s[kTM][kKC + 1];
   __shared__ float w_s[kKC][NC * 16];
   __shared__ int idx_s[kTM];
@@ -52,6 +52,7 @@ k_conv_rows(const float* __restrict__ in, int64_t ldi, const float* __restrict__
       if (t < kTM && row0 + t < n) {
         if (parent != nullptr) e = (my_kofs == k) ? my_parent : -1;
         else if (table != nullptr) e = table[(int64_t)k * ld + row0 + t];
+        else if (geom.mode != 0) e = dense_index(geom, row0 + t, k);
         else e = row0 + t;
       }
       __syncthreads();  // previous offset's readers of idx_s / in_s / w_s are done
@@ -106,7 +107,8 @@ k_conv_rows(const float* __restrict__ in, int64_t ldi, const float* __restrict__
           const int c = c0 + 16 * m;
           if (c < Cout) {
             float* p = out + (int64_t)r * ldo + c;
-            *p = accumulate ? (*p + acc[j][m]) : acc[j][m];
+            const float v = acc[j][m] + (bias != nullptr ? __ldg(bias + c) : 0.f);
+            *p = accumulate ? (*p + v) : v;
           }
         }
       }
@@ -119,15 +121,15 @@ template <int NC>
 void launch_rows(int grid, cudaStream_t st, const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si,
                  int64_t w_so, int kflip, const int32_t* table, int64_t ld, const int32_t* parent,
                  const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int Cin, int Cout, float* out,
-                 int64_t ldo, int accumulate) {
+                 int64_t ldo, int accumulate, const DenseGeom& geom, const float* bias) {
   k_conv_rows<NC><<<grid, kThreads, 0, st>>>(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, parent, kofs, K, n_cap,
-                                             n_dev, Cin, Cout, out, ldo, accumulate);
+                                             n_dev, Cin, Cout, out, ldo, accumulate, geom, bias);
 }
 
 int conv_rows_dispatch(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
                        int kflip, const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs,
                        int K, int64_t n_cap, const int32_t* n_dev, int Cin, int Cout, float* out, int64_t ldo,
-                       int accumulate, cudaStream_t st) {
+                       int accumulate, cudaStream_t st, const DenseGeom& geom = DenseGeom{}, const float* bias = nullptr) {
   if (n_cap == 0) return 0;
   int64_t g64 = cdiv(n_cap, kTM);
   const int64_t gmax = (int64_t)sm_count() * 8;
@@ -137,9 +139,10 @@ int conv_rows_dispatch(const float* in, int64_t ldi, const float* W, int64_t w_s
     const int nc = (co + 15) / 16;
     const float* Wb = W + (int64_t)cb * w_so;
     float* ob = out + cb;
+    const float* bb = bias ? bias + cb : nullptr;
 #define B200_ROWS(NCV)                                                                                          \
   launch_rows<NCV>(grid, st, in, ldi, Wb, w_sk, w_si, w_so, kflip, table, ld, parent, kofs, K, n_cap, n_dev, Cin, \
-                   co, ob, ldo, accumulate)
+                   co, ob, ldo, accumulate, geom, bb)
     switch (nc) {
       case 1: B200_ROWS(1); break;
       case 2: B200_ROWS(2); break;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(kThreads)
 k_wgrad_partial(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                 const int32_t* __restrict__ table, int64_t ld, int K, int gather_b, int64_t n_cap,
                 const int32_t* __restrict__ n_dev, int Ca, int Cb, int tiles_a, int tiles_b, int rows_per_split,
-                float* __restrict__ part) {
+                float* __restrict__ part, const DenseGeom geom) {
   __shared__ __align__(16) float a_s[kWR][kWT];
   __shared__ __align__(16) float b_s[kWR][kWT];
   __shared__ int ia_s[kWR], ib_s[kWR];
@@ -192,7 +195,7 @@ k_wgrad_partial(const float* __restrict__ A, int64_t lda, const float* __restric
   for (int r0 = r_begin; r0 < r_end; r0 += kWR) {
     // compact the valid (ra, rb) pairs of this row chunk, preserving row order
     int e = -1, r = r0 + t;
-    if (t < kWR && r < r_end) e = table ? table[(int64_t)k * ld + r] : r;
+    if (t < kWR && r < r_end) e = table ? table[(int64_t)k * ld + r] : (geom.mode != 0 ? dense_index(geom, r, k) : r);
     unsigned m = 0;
     if (t < 32 * (kWR / 32)) m = __ballot_sync(0xffffffffu, e >= 0);
     __syncthreads();  // previous chunk's readers done
@@ -290,6 +293,13 @@ int conv_parent_simt(const float* in, int64_t ldi, const float* W, int64_t w_sk,
                             ldo, 0, st);
 }
 
+int conv_dense_simt(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so, int K,
+                    int64_t n_out, int Cin, int Cout, float* out, int64_t ldo, const DenseGeom& geom, const float* bias,
+                    cudaStream_t st) {
+  return conv_rows_dispatch(in, ldi, W, w_sk, w_si, w_so, 0, nullptr, 0, nullptr, nullptr, K, n_out, nullptr, Cin, Cout,
+                            out, ldo, 0, st, geom, bias);
+}
+
 int64_t wgrad_scratch_bytes_simt(int64_t n_cap, int K, int Ca, int Cb) {
   int ns, rps;
   wgrad_plan(n_cap < 1 ? 1 : n_cap, K, Ca, Cb, &ns, &rps);
@@ -298,7 +308,7 @@ int64_t wgrad_scratch_bytes_simt(int64_t n_cap, int K, int Ca, int Cb) {
 
 int wgrad_table_simt(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* table, int64_t ld, int K,
                      int gather_b, int64_t n_cap, const int32_t* n_dev, int Ca, int Cb, float* dW, int accumulate,
-                     void* scratch, int64_t scratch_bytes, cudaStream_t st) {
+                     void* scratch, int64_t scratch_bytes, cudaStream_t st, const DenseGeom& geom) {
   const int64_t elems = (int64_t)K * Ca * Cb;
   if (n_cap == 0) {
     if (!accumulate) B200_CUDA(cudaMemsetAsync(dW, 0, (size_t)elems * 4, st));
@@ -311,7 +321,7 @@ int wgrad_table_simt(const float* A, int64_t lda, const float* B, int64_t ldb, c
   const int tiles_a = (Ca + kWT - 1) / kWT, tiles_b = (Cb + kWT - 1) / kWT;
   dim3 grid(K * tiles_a * tiles_b, ns);
   k_wgrad_partial<<<grid, kThreads, 0, st>>>(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, tiles_a,
-                                             tiles_b, rps, reinterpret_cast<float*>(scratch));
+                                             tiles_b, rps, reinterpret_cast<float*>(scratch), geom);
   int64_t g = cdiv(elems, 256);
   if (g > 1024) g = 1024;
   k_wgrad_reduce<<<(int)g, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), elems, rps, ns, n_cap, n_dev, dW,

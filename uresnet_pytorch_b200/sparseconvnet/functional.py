@@ -174,7 +174,7 @@ class BatchNormAct(torch.autograd.Function):
             mean = torch.empty(C, dtype=torch.float32, device=x.device)
             invstd = torch.empty(C, dtype=torch.float32, device=x.device)
             _lib.call("b200scn_bn_fwd_train", x.data_ptr(), x.stride(0), rows, n_dev, C, _lib.ptr(weight),
-                      _lib.ptr(bias), running_mean.data_ptr(), running_var.data_ptr(), eps, retention, leak,
+                      _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), eps, retention, leak,
                       y.data_ptr(), y.stride(0), mean.data_ptr(), invstd.data_ptr(), scratch.data_ptr(), nbytes,
                       _stream())
         else:
