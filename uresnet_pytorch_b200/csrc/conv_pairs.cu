@@ -37,6 +37,7 @@ struct PairParams {
   int64_t n_cap; const int32_t* n_dev;
   float* out; int64_t ldo; int accumulate; int x3;
   int warps;
+  int ksplit;  // > 1: the CTA's warps split the kernel offsets of ONE row tile (small inputs)
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -54,14 +55,15 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 
 // Q = Cin/16, MT = Cout tile/16, NCH = 32-row chunks per warp, WSMEM = weights in smem
 template <int Q, int MT, int NCH, bool WSMEM>
-__global__ void __launch_bounds__(NCH == 2 ? 512 : 128) k_conv_pairs(const PairParams p) {
+__global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairParams p) {
   constexpr int R = 32 * NCH, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
   constexpr int kQM = Q > MT ? Q : MT;
   constexpr int GB = kQM == 1 ? 4 : (kQM == 2 ? 2 : 1);  // 8-pair groups whose gathers are in flight together
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
-  if ((int64_t)blockIdx.x * warps * R >= n) return;
+  const int ksplit = p.ksplit;
+  if (ksplit > 1 ? ((int64_t)blockIdx.x * R >= n) : ((int64_t)blockIdx.x * warps * R >= n)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K;
@@ -106,7 +108,14 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 128) k_conv_pairs(const PairP
   }
 
   const int64_t n_tiles = ((int64_t)n + R - 1) / R;
-  for (int64_t wt = (int64_t)blockIdx.x * warps + warp; wt < n_tiles; wt += (int64_t)gridDim.x * warps) {
+  // ksplit == 1: every warp owns its own row tiles.  ksplit > 1: all warps of the CTA work on the
+  // same tile, warp w taking offsets w, w + ksplit, ... into a private accumulator; the partial
+  // accumulators are summed in fixed warp order at the end (deterministic).
+  const int kw = ksplit > 1 ? warp : 0;
+  const int kstep = ksplit > 1 ? ksplit : 1;
+  const int64_t wt0 = ksplit > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * warps + warp;
+  const int64_t wt_stride = ksplit > 1 ? (int64_t)gridDim.x : (int64_t)gridDim.x * warps;
+  for (int64_t wt = wt0; wt < n_tiles; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
     for (int e = lane; e < R * AS / 4; e += 32) reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,41 +259,55 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 128) k_conv_pairs(const PairP
     int T0[NCH], T1[NCH], T2[NCH];
     float4 G0[GB][Q], G1[GB][Q];
     int cnt0 = 0, cnt1 = 0;
+    // this warp's offsets are ko(j) = kw + j * kstep, j = 0 .. Kl-1
+    const int Kl = kw < K ? (K - kw + kstep - 1) / kstep : 0;
     {
       int Tc[NCH];
-      load_tbl(0, Tc);
-      load_tbl(1, T0);
-      load_tbl(2, T1);
-      load_tbl(3, T2);
+      load_tbl(kw, Tc);
+      load_tbl(kw + kstep, T0);
+      load_tbl(kw + 2 * kstep, T1);
+      load_tbl(kw + 3 * kstep, T2);
       cnt0 = compact(Tc, 0);
       gather(0, cnt0, 0, G0);
     }
-    for (int k = 0; k < K; k += 2) {
-      if (k + 1 < K) {
+    for (int j = 0; j < Kl; j += 2) {
+      if (j + 1 < Kl) {
         cnt1 = compact(T0, 1);
         gather(1, cnt1, 0, G1);
       }
-      compute(k, G0, 0, cnt0);
-      if (k + 1 >= K) break;
-      // T1 holds table[k+2], T2 holds table[k+3]; refill T0 with table[k+4]
-      if (k + 2 < K) {
+      compute(kw + j * kstep, G0, 0, cnt0);
+      if (j + 1 >= Kl) break;
+      // T1 holds offset j+2, T2 holds offset j+3; refill with offsets j+4, j+5
+      if (j + 2 < Kl) {
         cnt0 = compact(T1, 0);
         gather(0, cnt0, 0, G0);
       }
-      compute(k + 1, G1, 1, cnt1);
+      compute(kw + (j + 1) * kstep, G1, 1, cnt1);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) T0[c] = T2[c];
-      load_tbl(k + 4, T1);
-      load_tbl(k + 5, T2);
+      load_tbl(kw + (j + 4) * kstep, T1);
+      load_tbl(kw + (j + 5) * kstep, T2);
     }
 
-    // ---- epilogue: accumulator -> out, coalesced ---------------------------------------------------
+    // ---- epilogue: accumulator(s) -> out, coalesced ------------------------------------------------
     __syncwarp();
+    if (ksplit > 1) __syncthreads();
     const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    for (int e = lane; e < R * (CT / 4); e += 32) {
+    const int e_begin = ksplit > 1 ? tid : lane, e_step = ksplit > 1 ? (int)blockDim.x : 32;
+    for (int e = e_begin; e < R * (CT / 4); e += e_step) {
       const int row = e / (CT / 4), c4 = e - row * (CT / 4);
       if (base + row < n) {
-        float4 v = *reinterpret_cast<const float4*>(acc + row * AS + 4 * c4);
+        float4 v;
+        if (ksplit > 1) {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int w = 0; w < ksplit; ++w) {
+            const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wbase + (size_t)w * kPerWarp) +
+                                                              row * AS + 4 * c4);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+          }
+        } else {
+          v = *reinterpret_cast<const float4*>(acc + row * AS + 4 * c4);
+        }
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
         if (vec_ok) {
           if (p.accumulate) {
@@ -298,11 +321,12 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 128) k_conv_pairs(const PairP
         }
       }
     }
+    if (ksplit > 1) __syncthreads();  // partial accumulators are re-zeroed by the next tile
   }
 }
 
 struct PPlan {
-  int Q, MT, NCH, passes, warps, ctas_per_sm;
+  int Q, MT, NCH, passes, warps, ctas_per_sm, ksplit;
   bool wsmem, ok;
   size_t smem;
 };
@@ -329,8 +353,10 @@ PPlan plan_pairs(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   const size_t wbytes = (size_t)K * Cin * 16 * pl.MT * 4 * (x3 ? 2 : 1);
   pl.wsmem = large && (wbytes + 8 * pw <= (size_t)kMaxSmem);
   const size_t fixed = pl.wsmem ? wbytes : 0;
-  int warps = large ? 16 : 4;
-  while (warps > 2 && fixed + warps * pw > (size_t)kMaxSmem) warps >>= 1;
+  // small inputs: one row tile per CTA, its warps split the offsets (27 -> 9 warps x 3, 8 -> 4 x 2, ...)
+  pl.ksplit = large ? 1 : (K >= 27 ? 9 : (K >= 8 ? 4 : (K >= 4 ? 2 : 1)));
+  int warps = large ? 16 : (pl.ksplit > 1 ? pl.ksplit : 4);
+  while (pl.ksplit == 1 && warps > 2 && fixed + warps * pw > (size_t)kMaxSmem) warps >>= 1;
   if (fixed + warps * pw > (size_t)kMaxSmem) return pl;
   pl.warps = warps;
   pl.smem = fixed + warps * pw;
@@ -354,7 +380,7 @@ int launch_pairs(const PairParams& p, const PPlan& pl, cudaStream_t st) {
   }
   const int R = 32 * NCH;
   const int64_t tiles = cdiv(p.n_cap, R);
-  int64_t gx = cdiv(tiles, pl.warps);
+  int64_t gx = pl.ksplit > 1 ? tiles : cdiv(tiles, pl.warps);
   int64_t gmax = ((int64_t)sm_count() * pl.ctas_per_sm) / pl.passes;
   if (!WSMEM) gmax = (int64_t)sm_count() * pl.ctas_per_sm;  // no per-CTA prologue: no reason to hold CTAs back
   if (gmax < 1) gmax = 1;
@@ -413,6 +439,7 @@ int conv_rows_pairs(const float* in, int64_t ldi, const float* W, int64_t w_sk, 
     p.kflip = kflip; p.table = table; p.ld = ld; p.parent = parent; p.kofs = kofs; p.K = K; p.n_cap = n_cap;
     p.n_dev = n_dev; p.out = out; p.ldo = ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.x3 = x3;
     p.warps = pl.warps;
+    p.ksplit = pl.ksplit;
     int rc;
     switch (pl.Q) {
       case 1: rc = launch_q<1>(p, pl, st); break;
