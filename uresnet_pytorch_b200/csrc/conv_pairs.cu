@@ -40,11 +40,10 @@ struct PairParams {
   int ksplit;  // > 1: the CTA's warps split the kernel offsets of ONE row tile (small inputs)
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// tf32 "hi" part by truncation (one LOP3; cvt.rna.tf32 expands to ~4 ALU ops on sm_100).  With
+// the 3-term split the remainder v - hi is exact, so truncation costs no accuracy; in the
+// single-pass mode it is the tensor core's own operand truncation made explicit.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -53,12 +52,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+constexpr int kKB = 9;  // kernel offsets whose rule pairs are listed together (one "batch")
+
 // Q = Cin/16, MT = Cout tile/16, NCH = 32-row chunks per warp, WSMEM = weights in smem
 template <int Q, int MT, int NCH, bool WSMEM>
 __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairParams p) {
   constexpr int R = 32 * NCH, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
-  constexpr int kQM = Q > MT ? Q : MT;
-  constexpr int GB = kQM == 1 ? 4 : (kQM == 2 ? 2 : 1);  // 8-pair groups whose gathers are in flight together
+  constexpr int CAP = kKB * R;                // list slots per batch (every offset padded to a multiple of 8)
+  constexpr int DEPTH = Q == 1 ? 4 : 2;       // 8-pair groups whose gathers are in flight
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
@@ -75,12 +76,13 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
   float* Whi = reinterpret_cast<float*>(smem_raw);
   float* Wlo = Whi + w_elems;  // only filled / read when p.x3
   unsigned char* wbase = smem_raw + (size_t)w_elems * 4 * (p.x3 ? 2 : 1);
-  constexpr size_t kAccBytes = (size_t)R * AS * 4;
-  constexpr size_t kListBytes = (size_t)2 * R * 4 + (size_t)2 * R;  // in_s int32[2][R] + out_s uint8[2][R]
+  constexpr size_t kAccBytes = (size_t)(R + 1) * AS * 4;  // + 1 dummy row that absorbs the padding slots
+  constexpr size_t kListBytes = (size_t)CAP * 4 + (size_t)CAP + (size_t)CAP / 8;
   constexpr size_t kPerWarp = (kAccBytes + kListBytes + 15) & ~(size_t)15;
   float* acc = reinterpret_cast<float*>(wbase + (size_t)warp * kPerWarp);
   int32_t* in_s = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(acc) + kAccBytes);
-  uint8_t* out_s = reinterpret_cast<uint8_t*>(in_s + 2 * R);
+  uint8_t* out_s = reinterpret_cast<uint8_t*>(in_s + CAP);
+  uint8_t* gk_s = out_s + CAP;
 
   if (WSMEM) {
     // coalesced read along the contiguous weight dimension, scatter into A-fragment order
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
       const int mt = col >> 4, c = col & 15, gg = c & 7;
       const int r = ((rem & 1) << 1) | (c >> 3);
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r;
-      const float hi = __uint_as_float(to_tf32(v));
+      const float hi = tf32_hi(v);
       Whi[dst] = hi;
       if (p.x3) Wlo[dst] = v - hi;
     }
@@ -115,12 +117,14 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
   const int kstep = ksplit > 1 ? ksplit : 1;
   const int64_t wt0 = ksplit > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * warps + warp;
   const int64_t wt_stride = ksplit > 1 ? (int64_t)gridDim.x : (int64_t)gridDim.x * warps;
+  const int Kl = kw < K ? (K - kw + kstep - 1) / kstep : 0;  // this warp's offsets: kw + j * kstep
+
   for (int64_t wt = wt0; wt < n_tiles; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
-    for (int e = lane; e < R * AS / 4; e += 32) reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lane; e < (R + 1) * AS / 4; e += 32)
+      reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- rule-table entries of this warp's rows -------------------------------------------
     int pk[NCH], pp[NCH];
     if (p.parent != nullptr) {
 #pragma unroll
@@ -130,163 +134,136 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
         if (row < n) { pk[c] = p.kofs[row]; pp[c] = __ldg(p.parent + row); }
       }
     }
-    auto load_tbl = [&](int k, int (&dst)[NCH]) {
+
+    for (int j0 = 0; j0 < Kl; j0 += kKB) {
+      // ---- phase 1: list the rule pairs of up to kKB offsets, each offset padded to 8 slots ----
+      int ev[kKB][NCH];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int row = base + 32 * c + lane;
-        int e = -1;
-        if (k < K && row < n) {
-          if (p.parent != nullptr) e = (pk[c] == k) ? pp[c] : -1;
-          else if (p.table != nullptr) e = __ldg(p.table + (int64_t)k * p.ld + row);
-          else e = row;
+      for (int jj = 0; jj < kKB; ++jj) {
+        const int k = kw + (j0 + jj) * kstep;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int row = base + 32 * c + lane;
+          int e = -1;
+          if (j0 + jj < Kl && row < n) {
+            if (p.parent != nullptr) e = (pk[c] == k) ? pp[c] : -1;
+            else if (p.table != nullptr) e = __ldg(p.table + (int64_t)k * p.ld + row);
+            else e = row;
+          }
+          ev[jj][c] = e;
         }
-        dst[c] = e;
       }
-    };
-    auto compact = [&](const int (&src)[NCH], int buf) -> int {
-      int cnt = 0;
+      __syncwarp();  // previous batch's readers of the lists are done
+      int total = 0;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const uint32_t m = __ballot_sync(0xffffffffu, src[c] >= 0);
-        if (src[c] >= 0) {
-          const int pos = cnt + __popc(m & lt_mask);
-          in_s[buf * R + pos] = src[c];
-          out_s[buf * R + pos] = (uint8_t)(32 * c + lane);
+      for (int jj = 0; jj < kKB; ++jj) {
+        if (j0 + jj < Kl) {
+          const int g_first = total >> 3;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t m = __ballot_sync(0xffffffffu, ev[jj][c] >= 0);
+            if (ev[jj][c] >= 0) {
+              const int pos = total + __popc(m & lt_mask);
+              in_s[pos] = ev[jj][c];
+              out_s[pos] = (uint8_t)(32 * c + lane);
+            }
+            total += __popc(m);
+          }
+          const int padn = (8 - (total & 7)) & 7;
+          if (lane < padn) {
+            in_s[total + lane] = -1;
+            out_s[total + lane] = (uint8_t)R;  // dummy accumulator row
+          }
+          total += padn;
+          const int g_new = (total >> 3) - g_first;
+          if (lane < g_new) gk_s[g_first + lane] = (uint8_t)(kw + (j0 + jj) * kstep);
         }
-        cnt += __popc(m);
       }
       __syncwarp();
-      return cnt;
-    };
-    auto gather = [&](int buf, int cnt, int gb0, float4 (&G)[GB][Q]) {
-#pragma unroll
-      for (int gi = 0; gi < GB; ++gi) {
-        const int pi = 8 * (gb0 + gi) + g;
-        const int idx = pi < cnt ? in_s[buf * R + pi] : -1;
+      const int ng = total >> 3;
+
+      // ---- phase 2: uniform loop over dense 8-pair groups ------------------------------------
+      float4 G[DEPTH][Q];
+      auto gather = [&](int grp, float4 (&dst)[Q]) {
+        const int idx = grp < ng ? in_s[8 * grp + g] : -1;
         const float* src = p.in + (int64_t)(idx >= 0 ? idx : 0) * p.ldi + 4 * t;
 #pragma unroll
-        for (int q = 0; q < Q; ++q)
-          G[gi][q] = idx >= 0 ? ldg_f4(src + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto compute = [&](int kk, float4 (&G)[GB][Q], int buf, int cnt) {
-      for (int gb0 = 0; 8 * gb0 < cnt; gb0 += GB) {
-        if (gb0 > 0) gather(buf, cnt, gb0, G);
-        const int ngr = min(GB, (cnt - 8 * gb0 + 7) >> 3);
-        float d[GB][MT][4];
+        for (int q = 0; q < Q; ++q) dst[q] = idx >= 0 ? ldg_f4(src + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
 #pragma unroll
-        for (int gi = 0; gi < GB; ++gi)
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) d[gi][mt][r] = 0.f;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int s = 2 * q + h;
-            uint32_t ah[MT][4], al[MT][4];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              if (WSMEM) {
-                const int off = (((kk * KS + s) * MT + mt) * 32 + lane) * 4;
-                const float4 a4 = *reinterpret_cast<const float4*>(Whi + off);
-                ah[mt][0] = __float_as_uint(a4.x); ah[mt][1] = __float_as_uint(a4.y);
-                ah[mt][2] = __float_as_uint(a4.z); ah[mt][3] = __float_as_uint(a4.w);
-                if (p.x3) {
-                  const float4 l4 = *reinterpret_cast<const float4*>(Wlo + off);
-                  al[mt][0] = __float_as_uint(l4.x); al[mt][1] = __float_as_uint(l4.y);
-                  al[mt][2] = __float_as_uint(l4.z); al[mt][3] = __float_as_uint(l4.w);
-                }
-              } else {
-                const int kw = p.kflip ? (K - 1 - kk) : kk;
-                const float* wp = p.W + (int64_t)kw * p.w_sk + (int64_t)(16 * q + 4 * t + 2 * h) * p.w_si +
-                                  (int64_t)(cob + 16 * mt + g) * p.w_so;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                  const float v = __ldg(wp + (int64_t)(r >> 1) * p.w_si + (int64_t)(8 * (r & 1)) * p.w_so);
-                  ah[mt][r] = to_tf32(v);
-                  al[mt][r] = __float_as_uint(v - __uint_as_float(ah[mt][r]));
-                }
-              }
-            }
-#pragma unroll
-            for (int gi = 0; gi < GB; ++gi) {
-              if (gi < ngr) {
-                const float bx = h ? G[gi][q].z : G[gi][q].x;
-                const float by = h ? G[gi][q].w : G[gi][q].y;
-                const uint32_t b0 = to_tf32(bx), b1 = to_tf32(by);
-                if (p.x3) {
-                  const uint32_t l0 = __float_as_uint(bx - __uint_as_float(b0));
-                  const uint32_t l1 = __float_as_uint(by - __uint_as_float(b1));
-#pragma unroll
-                  for (int mt = 0; mt < MT; ++mt) {
-                    mma_tf32(d[gi][mt], al[mt], b0, b1);
-                    mma_tf32(d[gi][mt], ah[mt], l0, l1);
-                  }
-                }
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) mma_tf32(d[gi][mt], ah[mt], b0, b1);
-              }
-            }
-          }
-        }
-        // accumulate D^T fragments into the warp's output rows
-#pragma unroll
-        for (int gi = 0; gi < GB; ++gi) {
-          if (gi < ngr) {
-            const int p0 = 8 * (gb0 + gi) + 2 * t;
-            const int o0 = p0 < cnt ? out_s[buf * R + p0] : -1;
-            const int o1 = p0 + 1 < cnt ? out_s[buf * R + p0 + 1] : -1;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              if (o0 >= 0) {
-                acc[o0 * AS + 16 * mt + g] += d[gi][mt][0];
-                acc[o0 * AS + 16 * mt + g + 8] += d[gi][mt][2];
-              }
-              if (o1 >= 0) {
-                acc[o1 * AS + 16 * mt + g] += d[gi][mt][1];
-                acc[o1 * AS + 16 * mt + g + 8] += d[gi][mt][3];
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-    };
+      for (int d = 0; d < DEPTH; ++d) gather(d, G[d]);
 
-    // ---- software pipeline over the offsets ----------------------------------------------------
-    int T0[NCH], T1[NCH], T2[NCH];
-    float4 G0[GB][Q], G1[GB][Q];
-    int cnt0 = 0, cnt1 = 0;
-    // this warp's offsets are ko(j) = kw + j * kstep, j = 0 .. Kl-1
-    const int Kl = kw < K ? (K - kw + kstep - 1) / kstep : 0;
-    {
-      int Tc[NCH];
-      load_tbl(kw, Tc);
-      load_tbl(kw + kstep, T0);
-      load_tbl(kw + 2 * kstep, T1);
-      load_tbl(kw + 3 * kstep, T2);
-      cnt0 = compact(Tc, 0);
-      gather(0, cnt0, 0, G0);
-    }
-    for (int j = 0; j < Kl; j += 2) {
-      if (j + 1 < Kl) {
-        cnt1 = compact(T0, 1);
-        gather(1, cnt1, 0, G1);
-      }
-      compute(kw + j * kstep, G0, 0, cnt0);
-      if (j + 1 >= Kl) break;
-      // T1 holds offset j+2, T2 holds offset j+3; refill with offsets j+4, j+5
-      if (j + 2 < Kl) {
-        cnt0 = compact(T1, 0);
-        gather(0, cnt0, 0, G0);
-      }
-      compute(kw + (j + 1) * kstep, G1, 1, cnt1);
+      for (int g0 = 0; g0 < ng; g0 += DEPTH) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) T0[c] = T2[c];
-      load_tbl(kw + (j + 4) * kstep, T1);
-      load_tbl(kw + (j + 5) * kstep, T2);
+        for (int d = 0; d < DEPTH; ++d) {
+          const int grp = g0 + d;
+          if (grp < ng) {
+            const int kk = gk_s[grp];
+            float dacc[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) dacc[mt][r] = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              const float bv[4] = {G[d][q].x, G[d][q].y, G[d][q].z, G[d][q].w};
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int s = 2 * q + h;
+                const float bx = bv[2 * h], by = bv[2 * h + 1];
+                const float bxh = tf32_hi(bx), byh = tf32_hi(by);
+                const uint32_t b0 = __float_as_uint(bxh), b1 = __float_as_uint(byh);
+                const uint32_t l0 = __float_as_uint(bx - bxh), l1 = __float_as_uint(by - byh);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  uint32_t ah[4], al[4];
+                  if (WSMEM) {
+                    const int off = (((kk * KS + s) * MT + mt) * 32 + lane) * 4;
+                    const float4 a4 = *reinterpret_cast<const float4*>(Whi + off);
+                    ah[0] = __float_as_uint(a4.x); ah[1] = __float_as_uint(a4.y);
+                    ah[2] = __float_as_uint(a4.z); ah[3] = __float_as_uint(a4.w);
+                    if (p.x3) {
+                      const float4 l4 = *reinterpret_cast<const float4*>(Wlo + off);
+                      al[0] = __float_as_uint(l4.x); al[1] = __float_as_uint(l4.y);
+                      al[2] = __float_as_uint(l4.z); al[3] = __float_as_uint(l4.w);
+                    }
+                  } else {
+                    const int kwt = p.kflip ? (K - 1 - kk) : kk;
+                    const float* wp = p.W + (int64_t)kwt * p.w_sk + (int64_t)(16 * q + 4 * t + 2 * h) * p.w_si +
+                                      (int64_t)(cob + 16 * mt + g) * p.w_so;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                      const float v = __ldg(wp + (int64_t)(r >> 1) * p.w_si + (int64_t)(8 * (r & 1)) * p.w_so);
+                      const float vh = tf32_hi(v);
+                      ah[r] = __float_as_uint(vh);
+                      al[r] = __float_as_uint(v - vh);
+                    }
+                  }
+                  if (p.x3) {
+                    mma_tf32(dacc[mt], al, b0, b1);
+                    mma_tf32(dacc[mt], ah, l0, l1);
+                  }
+                  mma_tf32(dacc[mt], ah, b0, b1);
+                }
+              }
+            }
+            // this group's buffer is free: fetch the group DEPTH ahead
+            gather(grp + DEPTH, G[d]);
+            // D^T fragment -> accumulator rows (padding slots land in the dummy row)
+            const int o0 = out_s[8 * grp + 2 * t], o1 = out_s[8 * grp + 2 * t + 1];
+            float* a0 = acc + o0 * AS + g;
+            float* a1 = acc + o1 * AS + g;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              a0[16 * mt] += dacc[mt][0];
+              a0[16 * mt + 8] += dacc[mt][2];
+              a1[16 * mt] += dacc[mt][1];
+              a1[16 * mt + 8] += dacc[mt][3];
+            }
+            __syncwarp();
+          }
+        }
+      }
     }
 
     // ---- epilogue: accumulator(s) -> out, coalesced ------------------------------------------------
@@ -301,8 +278,8 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
         if (ksplit > 1) {
           v = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int w = 0; w < ksplit; ++w) {
-            const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wbase + (size_t)w * kPerWarp) +
-                                                              row * AS + 4 * c4);
+            const float4 u = *reinterpret_cast<const float4*>(
+                reinterpret_cast<const float*>(wbase + (size_t)w * kPerWarp) + row * AS + 4 * c4);
             v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
           }
         } else {
@@ -332,8 +309,8 @@ struct PPlan {
 };
 
 size_t per_warp_bytes(int MT, int NCH) {
-  const int R = 32 * NCH, AS = 16 * MT + 8;
-  size_t b = (size_t)R * AS * 4 + (size_t)2 * R * 4 + (size_t)2 * R;
+  const int R = 32 * NCH, AS = 16 * MT + 8, CAP = kKB * R;
+  size_t b = (size_t)(R + 1) * AS * 4 + (size_t)CAP * 4 + (size_t)CAP + (size_t)CAP / 8;
   return (b + 15) & ~(size_t)15;
 }
 
