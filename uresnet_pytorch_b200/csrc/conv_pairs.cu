@@ -28,14 +28,15 @@ namespace {
 
 constexpr int kMaxSmem = 220 * 1024;
 
+// strides are 32-bit on the device (checked on the host): address math stays in IMAD.WIDE form
 struct PairParams {
-  const float* in; int64_t ldi;
-  const float* W; int64_t w_sk, w_si, w_so; int kflip;
-  const int32_t* table; int64_t ld;
+  const float* in; int ldi;
+  const float* W; int w_sk, w_si, w_so; int kflip;
+  const int32_t* table; int ld;
   const int32_t* parent; const uint8_t* kofs;
   int K;
   int64_t n_cap; const int32_t* n_dev;
-  float* out; int64_t ldo; int accumulate; int x3;
+  float* out; int ldo; int accumulate; int x3;
   int warps;
   int ksplit;  // > 1: the CTA's warps split the kernel offsets of ONE row tile (small inputs)
 };
@@ -56,7 +57,7 @@ constexpr int kKB = 9;  // kernel offsets whose rule pairs are listed together (
 
 // Q = Cin/16, MT = Cout tile/16, NCH = 32-row chunks per warp, WSMEM = weights in smem
 template <int Q, int MT, int NCH, bool WSMEM>
-__global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairParams p) {
+__global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_pairs(const PairParams p) {
   constexpr int R = 32 * NCH, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
   constexpr int CAP = kKB * R;                // list slots per batch (every offset padded to a multiple of 8)
   constexpr int DEPTH = Q == 1 ? 4 : 2;       // 8-pair groups whose gathers are in flight
@@ -79,10 +80,12 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
   constexpr size_t kAccBytes = (size_t)(R + 1) * AS * 4;  // + 1 dummy row that absorbs the padding slots
   constexpr size_t kListBytes = (size_t)CAP * 4 + (size_t)CAP + (size_t)CAP / 8;
   constexpr size_t kPerWarp = (kAccBytes + kListBytes + 15) & ~(size_t)15;
-  float* acc = reinterpret_cast<float*>(wbase + (size_t)warp * kPerWarp);
-  int32_t* in_s = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(acc) + kAccBytes);
-  uint8_t* out_s = reinterpret_cast<uint8_t*>(in_s + CAP);
-  uint8_t* gk_s = out_s + CAP;
+  // per-warp regions addressed as 32-bit offsets from the shared window (no 64-bit generic pointers)
+  const int warp_off = (int)((size_t)w_elems * 4 * (p.x3 ? 2 : 1)) + warp * (int)kPerWarp;  // bytes
+  float* const acc = reinterpret_cast<float*>(smem_raw + warp_off);
+  int32_t* const in_s = reinterpret_cast<int32_t*>(smem_raw + warp_off + (int)kAccBytes);
+  uint8_t* const out_s = smem_raw + warp_off + (int)kAccBytes + CAP * 4;
+  uint8_t* const gk_s = smem_raw + warp_off + (int)kAccBytes + CAP * 4 + CAP;
 
   if (WSMEM) {
     // coalesced read along the contiguous weight dimension, scatter into A-fragment order
@@ -135,29 +138,38 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
       }
     }
 
-    for (int j0 = 0; j0 < Kl; j0 += kKB) {
-      // ---- phase 1: list the rule pairs of up to kKB offsets, each offset padded to 8 slots ----
-      int ev[kKB][NCH];
+    int ev[kKB][NCH];
+    bool row_ok[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) row_ok[c] = base + 32 * c + lane < n;
+    const int32_t* tptr = p.table != nullptr ? p.table + (int64_t)kw * p.ld + base + lane : nullptr;
+    const int tstep = kstep * p.ld;  // elements between this warp's consecutive offsets
+    auto load_batch = [&](int j0) {
+      const int nb = min(kKB, Kl - j0);
 #pragma unroll
       for (int jj = 0; jj < kKB; ++jj) {
-        const int k = kw + (j0 + jj) * kstep;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int row = base + 32 * c + lane;
           int e = -1;
-          if (j0 + jj < Kl && row < n) {
-            if (p.parent != nullptr) e = (pk[c] == k) ? pp[c] : -1;
-            else if (p.table != nullptr) e = __ldg(p.table + (int64_t)k * p.ld + row);
-            else e = row;
+          if (jj < nb && row_ok[c]) {
+            if (p.parent != nullptr) e = (pk[c] == kw + (j0 + jj) * kstep) ? pp[c] : -1;
+            else if (tptr != nullptr) e = __ldg(tptr + 32 * c);
+            else e = base + 32 * c + lane;
           }
           ev[jj][c] = e;
         }
+        if (tptr != nullptr) tptr += tstep;
       }
+    };
+    load_batch(0);
+    for (int j0 = 0; j0 < Kl; j0 += kKB) {
+      // ---- phase 1: list the rule pairs of up to kKB offsets, each offset padded to 8 slots ----
       __syncwarp();  // previous batch's readers of the lists are done
       int total = 0;
+      const int nb_cur = min(kKB, Kl - j0);
 #pragma unroll
       for (int jj = 0; jj < kKB; ++jj) {
-        if (j0 + jj < Kl) {
+        if (jj < nb_cur) {
           const int g_first = total >> 3;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -181,6 +193,7 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : 288) k_conv_pairs(const PairP
       }
       __syncwarp();
       const int ng = total >> 3;
+      load_batch(j0 + kKB);  // next batch's table entries travel while this batch is multiplied
 
       // ---- phase 2: uniform loop over dense 8-pair groups ------------------------------------
       float4 G[DEPTH][Q];
@@ -323,7 +336,7 @@ PPlan plan_pairs(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   const int cot = Cout / 16;
   pl.MT = cot % 4 == 0 ? 4 : (cot % 3 == 0 ? 3 : (cot % 2 == 0 ? 2 : 1));
   const bool large = n_cap >= 65536;
-  pl.NCH = large ? 2 : 1;
+  pl.NCH = (large && pl.Q * pl.MT > 2) ? 2 : 1;
   if (!large && pl.MT > 2) pl.MT = (cot % 2 == 0) ? 2 : 1;  // more, smaller tasks when rows are few
   pl.passes = cot / pl.MT;
   const size_t pw = per_warp_bytes(pl.MT, pl.NCH);
@@ -332,7 +345,7 @@ PPlan plan_pairs(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   const size_t fixed = pl.wsmem ? wbytes : 0;
   // small inputs: one row tile per CTA, its warps split the offsets (27 -> 9 warps x 3, 8 -> 4 x 2, ...)
   pl.ksplit = large ? 1 : (K >= 27 ? 9 : (K >= 8 ? 4 : (K >= 4 ? 2 : 1)));
-  int warps = large ? 16 : (pl.ksplit > 1 ? pl.ksplit : 4);
+  int warps = large ? (pl.NCH == 1 ? 32 : 16) : (pl.ksplit > 1 ? pl.ksplit : 4);
   while (pl.ksplit == 1 && warps > 2 && fixed + warps * pw > (size_t)kMaxSmem) warps >>= 1;
   if (fixed + warps * pw > (size_t)kMaxSmem) return pl;
   pl.warps = warps;
@@ -376,6 +389,7 @@ int launch_qm(const PairParams& p, const PPlan& pl, cudaStream_t st) {
     if (pl.wsmem) return launch_pairs<Q, MT, 2, true>(p, pl, st);
     return launch_pairs<Q, MT, 2, false>(p, pl, st);
   }
+  if (pl.wsmem) return launch_pairs<Q, MT, 1, true>(p, pl, st);
   return launch_pairs<Q, MT, 1, false>(p, pl, st);
 }
 
@@ -391,8 +405,13 @@ int launch_q(const PairParams& p, const PPlan& pl, cudaStream_t st) {
 
 }  // namespace
 
-bool conv_pairs_supported(int Cin, int Cout, int K, int64_t ldi, const void* in) {
+bool conv_pairs_supported(int Cin, int Cout, int K, int64_t ldi, const void* in, int64_t n_cap, int64_t ld,
+                          int64_t ldo, int64_t n_in_max) {
   if (Cin % 16 != 0 || Cout % 16 != 0 || K < 1 || K > 64) return false;
+  // 32-bit element offsets on the device
+  const int64_t lim = (1ll << 31) - 1;
+  (void)n_in_max; (void)n_cap;
+  if (ldi >= lim || ldo >= lim || (int64_t)K * ld >= lim || (int64_t)K * Cin * Cout >= lim) return false;
   if (ldi % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0) return false;
   return true;
 }
@@ -412,9 +431,10 @@ int conv_rows_pairs(const float* in, int64_t ldi, const float* W, int64_t w_sk, 
       return B200SCN_ERR_UNSUPPORTED;
     }
     PairParams p;
-    p.in = in + c0; p.ldi = ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = w_sk; p.w_si = w_si; p.w_so = w_so;
-    p.kflip = kflip; p.table = table; p.ld = ld; p.parent = parent; p.kofs = kofs; p.K = K; p.n_cap = n_cap;
-    p.n_dev = n_dev; p.out = out; p.ldo = ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.x3 = x3;
+    p.in = in + c0; p.ldi = (int)ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = (int)w_sk; p.w_si = (int)w_si;
+    p.w_so = (int)w_so; p.kflip = kflip; p.table = table; p.ld = (int)ld; p.parent = parent; p.kofs = kofs; p.K = K;
+    p.n_cap = n_cap; p.n_dev = n_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate;
+    p.x3 = x3;
     p.warps = pl.warps;
     p.ksplit = pl.ksplit;
     int rc;
