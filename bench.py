@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true", help="keep wgrad kernels on the main stream")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-events", type=int, default=128)
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--math", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="fp32: FFMA kernels; tf32x3: tensor-core 3-term split, fp32-equivalent (parity-tested at the "
+                         "fp32 tolerances); tf32: single-pass tensor core (reduced precision)")
     return ap.parse_args()
 
 
@@ -347,7 +349,7 @@ def run_b200(args):
         "metric": "sparse U-ResNet train voxels/sec at 512^3", "value": vox_all / dev_s, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32x3": "f32 (tf32x3 mma)", "tf32": "tf32"}[args.math], "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (storage and accumulation fp32; products via 3-term tf32 split on mma.sync, fp32-equivalent: tests/test_gpu_mma.py)", "tf32": "tf32 (reduced precision)"}[args.math], "data": "synthetic",
         "config": {"workload": "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[1]), "
                                "Adam, fp32" % args.events_per_gpu,
                    "events_per_gpu": args.events_per_gpu, "mean_voxels_per_step_per_gpu": vox_all / world / args.steps,

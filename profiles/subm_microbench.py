@@ -10,7 +10,7 @@ import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--roofline-events", type=int, default=128)
-ap.add_argument("--math", default="fp32")
+ap.add_argument("--math", default="tf32x3")
 a = ap.parse_args()
 from uresnet_pytorch_b200 import sparseconvnet as scn  # noqa: E402
 mode = {"fp32": scn.MATH_FP32, "tf32x3": scn.MATH_TF32X3, "tf32": scn.MATH_TF32}[a.math]

@@ -15,6 +15,12 @@ namespace {
 
 constexpr int kRowsPerBlock = 128;
 
+// Ticket counters of the "last CTA folds the partials" pattern.  They live in the module (zero
+// at load) and the folding CTA resets them, so no memset has to precede a launch.  One counter
+// per kernel type is enough: launches of one type are stream-ordered on the caller's stream.
+__device__ unsigned int g_bn_fwd_ticket = 0;
+__device__ unsigned int g_bn_bwd_ticket = 0;
+
 struct Layout {
   int threads, RL, blocks;
 };
@@ -85,7 +91,7 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
   __threadfence();
   __syncthreads();
   if (t == 0) {
-    const unsigned ticket = atomicAdd(counter, 1u);
+    const unsigned ticket = atomicAdd(&g_bn_fwd_ticket, 1u);
     is_last = (ticket == (unsigned)nblk - 1u);
   }
   __syncthreads();
@@ -114,7 +120,7 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
       running_var[c] = retention * running_var[c] + (1.f - retention) * (S / fmaxf(N - 1.f, 1.f));
     }
   }
-  if (t == 0) *counter = 0u;
+  if (t == 0) g_bn_fwd_ticket = 0u;
 }
 
 __global__ void k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev,
@@ -179,7 +185,7 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
   __threadfence();
   __syncthreads();
   if (t == 0) {
-    const unsigned ticket = atomicAdd(counter, 1u);
+    const unsigned ticket = atomicAdd(&g_bn_bwd_ticket, 1u);
     is_last = (ticket == (unsigned)nblk - 1u);
   }
   __syncthreads();
@@ -205,7 +211,7 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
     dbeta[c] = a1;
     dgamma[c] = a2;
   }
-  if (t == 0) *counter = 0u;
+  if (t == 0) g_bn_bwd_ticket = 0u;
 }
 
 __global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
@@ -261,7 +267,6 @@ extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, 
   Layout L = make_layout(n_cap, C);
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  B200_CUDA(cudaMemsetAsync(counter, 0, 4, st));
   k_bn_stats<<<L.blocks, L.threads, 3 * L.threads * sizeof(float), st>>>(
       x, ldx, n_cap, n_dev, C, L.RL, part, counter, running_mean, running_var, eps, retention, save_mean, save_invstd);
   k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, save_mean,
@@ -301,7 +306,6 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
   Layout L = make_layout(n_cap, C);
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  B200_CUDA(cudaMemsetAsync(counter, 0, 4, st));
   k_bn_bwd_reduce<<<L.blocks, L.threads, 2 * L.threads * sizeof(float), st>>>(
       x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta, mean, invstd, leak, part, counter, dgamma, dbeta);
   k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta,

@@ -19,6 +19,11 @@ namespace {
 constexpr int kBatch = 64;  // pairs gathered per stage
 constexpr int kWarpsMax = 8;
 
+// per-(offset, column split) tickets: the last row-chunk CTA of an offset folds that offset's
+// partial blocks in chunk order (deterministic) -- no separate fold launch.  Zero at module load,
+// reset by the folding CTA.  wgrad launches are stream-ordered among themselves.
+__device__ unsigned int g_wgrad_ticket[64 * 8];
+
 struct WgParams {
   const float* A; int64_t lda;
   const float* B; int64_t ldb;
@@ -29,6 +34,7 @@ struct WgParams {
   int rows_per_cta;
   float* part;
   int x3;
+  float* dW; int accumulate;
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -59,7 +65,8 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
   const int n = live_rows(p.n_dev, p.n_cap);
   const int k = blockIdx.x;
   const int r_begin = blockIdx.y * p.rows_per_cta;
-  if (r_begin >= n) return;
+  const int live_chunks = max(1, min((int)gridDim.y, (n + p.rows_per_cta - 1) / p.rows_per_cta));
+  if ((int)blockIdx.y >= live_chunks) return;
   const int r_end = min(n, r_begin + p.rows_per_cta);
   const int cb0 = blockIdx.z * p.cb_per_z;                 // first output channel of this split
   const int Cbz = min(p.cb_per_z, p.Cb - cb0);             // output channels handled here
@@ -181,6 +188,27 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
       *reinterpret_cast<float2*>(dst + (int64_t)(ci + 8) * p.Cb + co) = make_float2(acc[i][2], acc[i][3]);
     }
   }
+
+  // ---- (5) the last chunk-CTA of this (offset, column split) folds the partial blocks -------------
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  unsigned int* ticket = &g_wgrad_ticket[(k & 63) * 8 + (blockIdx.z & 7)];
+  if (tid == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)live_chunks - 1u);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int64_t chunk_stride = (int64_t)p.K * Ca * p.Cb;
+  const float* src = p.part + (int64_t)k * Ca * p.Cb;
+  float* out = p.dW + (int64_t)k * Ca * p.Cb;
+  for (int e = tid; e < Ca * Cbz; e += nthr) {
+    const int ci = e / Cbz, co = cb0 + (e - ci * Cbz);
+    const int64_t off = (int64_t)ci * p.Cb + co;
+    float s = 0.f;
+    for (int c = 0; c < live_chunks; ++c) s += __ldcg(src + c * chunk_stride + off);
+    out[off] = p.accumulate ? out[off] + s : s;
+  }
+  if (tid == 0) *ticket = 0u;
 }
 
 __global__ void k_wgrad_fold(const float* __restrict__ part, int64_t elems, int rows_per_cta, int nchunks,
@@ -283,6 +311,8 @@ int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, co
   p.n_cap = n_cap; p.n_dev = n_dev; p.Ca = Ca; p.Cb = Cb; p.cb_per_z = pl.cb_per_z;
   p.rows_per_cta = pl.rows_per_cta; p.part = reinterpret_cast<float*>(scratch);
   p.x3 = (math_mode == B200SCN_MATH_TF32X3) ? 1 : 0;
+  p.dW = dW; p.accumulate = accumulate;
+  B200_CHECK_ARG(K <= 64 && pl.zsplits <= 8, "wgrad_mma: K > 64 or more than 8 column splits");
   int rc = 0;
   switch (pl.tpw) {
     case 1: rc = wg_launch<1>(p, pl, st); break;
@@ -292,11 +322,7 @@ int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, co
     default: rc = wg_launch<16>(p, pl, st); break;
   }
   if (rc) return rc;
-  int64_t gsz = cdiv(elems, 256);
-  if (gsz > 1024) gsz = 1024;
-  k_wgrad_fold<<<(int)gsz, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), elems, pl.rows_per_cta, pl.nchunks,
-                                         n_cap, n_dev, dW, accumulate);
-  count_launches(2);
+  count_launches(1);
   B200_CHECK_LAUNCH("wgrad_mma");
   return 0;
 }
