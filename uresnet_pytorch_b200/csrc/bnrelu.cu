@@ -8,18 +8,28 @@
 // partials are folded by the last CTA to finish (ticket counter), so no extra launch and no
 // host involvement.  Thread layout: thread = (column c, row lane rl); consecutive threads
 // read consecutive columns of a row -> coalesced for any C.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200scn {
 namespace {
 
-constexpr int kRowsPerBlock = 128;
-
-// Ticket counters of the "last CTA folds the partials" pattern.  They live in the module (zero
-// at load) and the folding CTA resets them, so no memset has to precede a launch.  One counter
-// per kernel type is enough: launches of one type are stream-ordered on the caller's stream.
-__device__ unsigned int g_bn_fwd_ticket = 0;
-__device__ unsigned int g_bn_bwd_ticket = 0;
+// Rows per partial-sum CTA: ~8192 elements per CTA (32 per thread), so narrow layers (many rows)
+// and wide layers (few rows) both produce a few dozen partials -- a short fold in the apply
+// kernels and enough CTAs to fill the SMs.  B200SCN_BN_ELEMS overrides the element budget.
+static int rows_per_block_host(int C) {
+  static int elems = 0;
+  if (elems == 0) {
+    const char* e = getenv("B200SCN_BN_ELEMS");
+    elems = e ? atoi(e) : 8192;
+    if (elems < 256) elems = 256;
+  }
+  int r = elems / C;
+  if (r < 16) r = 16;
+  if (r > 2048) r = 2048;
+  return r;
+}
 
 struct Layout {
   int threads, RL, blocks;
@@ -27,9 +37,16 @@ struct Layout {
 
 Layout make_layout(int64_t n_cap, int C) {
   Layout L;
-  L.RL = C >= 256 ? 1 : 256 / C;
+  static int tpb = 0;  // threads per CTA (B200SCN_BN_THREADS, default 1024): short per-thread chains
+  if (tpb == 0) {
+    const char* e = getenv("B200SCN_BN_THREADS");
+    tpb = e ? atoi(e) : 1024;
+    if (tpb < 64) tpb = 64;
+    if (tpb > 1024) tpb = 1024;
+  }
+  L.RL = C >= tpb ? 1 : tpb / C;
   L.threads = C * L.RL;
-  int64_t b = cdiv(n_cap, kRowsPerBlock);
+  int64_t b = cdiv(n_cap, rows_per_block_host(C));
   const int64_t cap = (int64_t)sm_count() * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -46,19 +63,39 @@ __device__ __forceinline__ void chan_merge(float& na, float& ma, float& sa, floa
   na = n;
 }
 
-// part layout: [blocks][3][C]  (count, mean, M2)
+// Merge the RL row lanes of every column held in sm[0..T), sm[T..2T), sm[2T..3T) (count, mean, M2)
+// with a fixed-shape binary tree (deterministic); the result ends up in lane 0 = sm[c], ...
+__device__ __forceinline__ void chan_tree_merge(float* sm, int T, int C, int RL, int c, int rl) {
+  int stride = 1;
+  while (stride < RL) stride <<= 1;
+  for (stride >>= 1; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (rl < stride && rl + stride < RL) {
+      const int a = rl * C + c, b = (rl + stride) * C + c;
+      float n = sm[a], m = sm[T + a], s = sm[2 * T + a];
+      chan_merge(n, m, s, sm[b], sm[T + b], sm[2 * T + b]);
+      sm[a] = n;
+      sm[T + a] = m;
+      sm[2 * T + a] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int live_blocks(int n, int grid_stats, int rows_per_blk) {
+  return max(1, min(grid_stats, (n + rows_per_blk - 1) / rows_per_blk));
+}
+
+// Pass 1 of the training forward: per-CTA (count, mean, M2) per column.  part layout [blocks][3][C].
+// No cross-CTA step here: every CTA of the apply kernel folds the partials itself (same order
+// everywhere, so all CTAs agree bit for bit) -- there is no serial "last CTA" phase.
 __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev,
-                           int C, int RL, float* __restrict__ part, unsigned int* counter, float* running_mean,
-                           float* running_var, float eps, float retention, float* __restrict__ save_mean,
-                           float* __restrict__ save_invstd) {
+                           int C, int RL, int rows_per_blk, float* __restrict__ part) {
   extern __shared__ float sm[];  // [3][threads]
-  __shared__ bool is_last;
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
-  // only as many CTAs as the live row count warrants take part (static regime: the grid is
-  // sized for the capacity); the others leave before touching the ticket
-  const int nblk = max(1, min((int)gridDim.x, (n + kRowsPerBlock - 1) / kRowsPerBlock));
+  const int nblk = live_blocks(n, (int)gridDim.x, rows_per_blk);
   if ((int)blockIdx.x >= nblk) return;
   const int rpb = (n + nblk - 1) / nblk;
   const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
@@ -80,24 +117,28 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
   sm[t] = cnt;
   sm[T + t] = mean;
   sm[2 * T + t] = m2;
-  __syncthreads();
+  chan_tree_merge(sm, T, C, RL, c, rl);
   if (rl == 0) {
-    for (int j = 1; j < RL; ++j) chan_merge(cnt, mean, m2, sm[j * C + c], sm[T + j * C + c], sm[2 * T + j * C + c]);
     float* p = part + (int64_t)blockIdx.x * 3 * C;
-    p[c] = cnt;
-    p[C + c] = mean;
-    p[2 * C + c] = m2;
+    p[c] = sm[c];
+    p[C + c] = sm[T + c];
+    p[2 * C + c] = sm[2 * T + c];
   }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {
-    const unsigned ticket = atomicAdd(&g_bn_fwd_ticket, 1u);
-    is_last = (ticket == (unsigned)nblk - 1u);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // fold the per-CTA partials: row lane rl takes CTAs rl, rl+RL, ...; lanes merged in order
+}
+
+// Pass 2: fold the partials (row lane rl takes CTAs rl, rl+RL, ...; lanes merged in order), then
+// y = act((x - mean) * invstd * gamma + beta).  CTA 0 also publishes the statistics.
+__global__ void k_bn_apply_train(const float* __restrict__ x, int64_t ldx, int64_t n_cap,
+                                 const int32_t* __restrict__ n_dev, int C, int RL, int rows_per_blk, int grid_stats,
+                                 const float* __restrict__ part, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* running_mean, float* running_var, float eps,
+                                 float retention, float leak, float* __restrict__ y, int64_t ldy,
+                                 float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  extern __shared__ float sm[];  // [3][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
     float N = 0.f, M = 0.f, S = 0.f;
     for (int b = rl; b < nblk; b += RL) {
@@ -108,19 +149,25 @@ __global__ void k_bn_stats(const float* __restrict__ x, int64_t ldx, int64_t n_c
     sm[T + t] = M;
     sm[2 * T + t] = S;
   }
-  __syncthreads();
-  if (rl == 0) {
-    float N = sm[c], M = sm[T + c], S = sm[2 * T + c];
-    for (int j = 1; j < RL; ++j) chan_merge(N, M, S, sm[j * C + c], sm[T + j * C + c], sm[2 * T + j * C + c]);
-    const float var_b = N > 0.f ? S / N : 0.f;
+  chan_tree_merge(sm, T, C, RL, c, rl);
+  const float N = sm[c], M = sm[T + c], S = sm[2 * T + c];
+  const float is = rsqrtf((N > 0.f ? S / N : 0.f) + eps);
+  if (blockIdx.x == 0 && rl == 0) {
     save_mean[c] = M;
-    save_invstd[c] = rsqrtf(var_b + eps);
+    save_invstd[c] = is;
     if (running_mean != nullptr) {
       running_mean[c] = retention * running_mean[c] + (1.f - retention) * M;
       running_var[c] = retention * running_var[c] + (1.f - retention) * (S / fmaxf(N - 1.f, 1.f));
     }
   }
-  if (t == 0) g_bn_fwd_ticket = 0u;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float scale = is * g;
+  const float shift = b - M * scale;
+  for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
+    float v = fmaf(__ldg(x + (int64_t)r * ldx + c), scale, shift);
+    v = v > 0.f ? v : v * leak;
+    y[(int64_t)r * ldy + c] = v;
+  }
 }
 
 __global__ void k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev,
@@ -142,19 +189,17 @@ __global__ void k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t n_c
   }
 }
 
-// part layout: [blocks][2][C]
+// Backward pass 1: per-CTA sums of dy_masked and dy_masked * xhat.  part layout [blocks][2][C]
 __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
-                                int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL,
+                                int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL, int rows_per_blk,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ mean, const float* __restrict__ invstd, float leak,
-                                float* __restrict__ part, unsigned int* counter, float* __restrict__ dgamma,
-                                float* __restrict__ dbeta) {
+                                float* __restrict__ part) {
   extern __shared__ float sm[];  // [2][threads]
-  __shared__ bool is_last;
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
-  const int nblk = max(1, min((int)gridDim.x, (n + kRowsPerBlock - 1) / kRowsPerBlock));
+  const int nblk = live_blocks(n, (int)gridDim.x, rows_per_blk);
   if ((int)blockIdx.x >= nblk) return;
   const int rpb = (n + nblk - 1) / nblk;
   const int r0 = blockIdx.x * rpb, r1 = min(n, r0 + rpb);
@@ -182,15 +227,20 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
     p[c] = s1;
     p[C + c] = s2;
   }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {
-    const unsigned ticket = atomicAdd(&g_bn_bwd_ticket, 1u);
-    is_last = (ticket == (unsigned)nblk - 1u);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+}
+
+// Backward pass 2: fold the partials (every CTA, same order), then dx.  CTA 0 writes dgamma / dbeta.
+__global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
+                               int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL, int rows_per_blk,
+                               int grid_stats, const float* __restrict__ part, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ invstd, float leak, int train, float* __restrict__ dgamma,
+                               float* __restrict__ dbeta, float* __restrict__ dx, int64_t lddx) {
+  extern __shared__ float sm[];  // [2][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
     float a1 = 0.f, a2 = 0.f;
     for (int bk = rl; bk < nblk; bk += RL) {
@@ -202,32 +252,20 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ x, int64_t ldx, const 
     sm[T + t] = a2;
   }
   __syncthreads();
-  if (rl == 0) {
-    float a1 = sm[c], a2 = sm[T + c];
-    for (int j = 1; j < RL; ++j) {
-      a1 += sm[j * C + c];
-      a2 += sm[T + j * C + c];
-    }
+  float a1 = sm[c], a2 = sm[T + c];
+  for (int j = 1; j < RL; ++j) {
+    a1 += sm[j * C + c];
+    a2 += sm[T + j * C + c];
+  }
+  if (blockIdx.x == 0 && rl == 0) {
     dbeta[c] = a1;
     dgamma[c] = a2;
   }
-  if (t == 0) g_bn_bwd_ticket = 0u;
-}
-
-__global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
-                               int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL,
-                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                               const float* __restrict__ mean, const float* __restrict__ invstd, float leak, int train,
-                               const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                               float* __restrict__ dx, int64_t lddx) {
-  const int n = live_rows(n_dev, n_cap);
-  const int t = threadIdx.x;
-  const int c = t % C, rl = t / C;
   const float mu = mean[c], is = invstd[c];
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
-  const float k1 = train ? dbeta[c] * inv_n : 0.f;
-  const float k2 = train ? dgamma[c] * inv_n : 0.f;
+  const float k1 = train ? a1 * inv_n : 0.f;
+  const float k2 = train ? a2 * inv_n : 0.f;
   const float gi = g * is;
   for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
     const float xh = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
@@ -265,12 +303,12 @@ extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, 
   B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_fwd_train: scratch too small");
   if (n_cap == 0) return 0;
   Layout L = make_layout(n_cap, C);
-  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  k_bn_stats<<<L.blocks, L.threads, 3 * L.threads * sizeof(float), st>>>(
-      x, ldx, n_cap, n_dev, C, L.RL, part, counter, running_mean, running_var, eps, retention, save_mean, save_invstd);
-  k_bn_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, n_cap, n_dev, C, L.RL, gamma, beta, save_mean,
-                                                            save_invstd, eps, 0, leak, y, ldy);
+  const int rpb = rows_per_block_host(C);
+  k_bn_stats<<<L.blocks, L.threads, 3 * L.threads * sizeof(float), st>>>(x, ldx, n_cap, n_dev, C, L.RL, rpb, part);
+  k_bn_apply_train<<<apply_grid(n_cap, L.RL), L.threads, 3 * L.threads * sizeof(float), st>>>(
+      x, ldx, n_cap, n_dev, C, L.RL, rpb, L.blocks, part, gamma, beta, running_mean, running_var, eps, retention, leak,
+      y, ldy, save_mean, save_invstd);
   count_launches(2);
   B200_CHECK_LAUNCH("bn_fwd_train");
   return 0;
@@ -304,12 +342,14 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
     return 0;
   }
   Layout L = make_layout(n_cap, C);
-  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  k_bn_bwd_reduce<<<L.blocks, L.threads, 2 * L.threads * sizeof(float), st>>>(
-      x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta, mean, invstd, leak, part, counter, dgamma, dbeta);
-  k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 0, st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, gamma, beta,
-                                                                mean, invstd, leak, train, dgamma, dbeta, dx, lddx);
+  const int rpb = rows_per_block_host(C);
+  k_bn_bwd_reduce<<<L.blocks, L.threads, 2 * L.threads * sizeof(float), st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL,
+                                                                              rpb, gamma, beta, mean, invstd, leak,
+                                                                              part);
+  k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 2 * L.threads * sizeof(float), st>>>(
+      x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, rpb, L.blocks, part, gamma, beta, mean, invstd, leak, train, dgamma,
+      dbeta, dx, lddx);
   count_launches(2);
   B200_CHECK_LAUNCH("bn_bwd");
   return 0;

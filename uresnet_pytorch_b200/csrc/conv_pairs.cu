@@ -57,7 +57,7 @@ constexpr int kKB = 9;  // kernel offsets whose rule pairs are listed together (
 
 // Q = Cin/16, MT = Cout tile/16, NCH = 32-row chunks per warp, WSMEM = weights in smem
 template <int Q, int MT, int NCH, bool WSMEM>
-__global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_pairs(const PairParams p) {
+__global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288), (NCH == 1 && !WSMEM) ? 2 : 1) k_conv_pairs(const PairParams p) {
   constexpr int R = 32 * NCH, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
   constexpr int CAP = kKB * R;                // list slots per batch (every offset padded to a multiple of 8)
   constexpr int DEPTH = Q == 1 ? 4 : 2;       // 8-pair groups whose gathers are in flight
@@ -71,6 +71,9 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
   const int K = p.K;
   const int cob = blockIdx.y * CT;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  // 8-byte weight loads are legal when the strides keep every (ci, co) pair start 8-byte aligned
+  const bool w_vec2 = ((reinterpret_cast<uintptr_t>(p.W) & 7) == 0) && (p.w_sk % 2 == 0) && (p.w_si % 2 == 0 || p.w_si == 1) &&
+                      (p.w_so % 2 == 0 || p.w_so == 1);
 
   // ---- shared memory carve-up ----------------------------------------------------------------
   const int w_elems = WSMEM ? K * KS * MT * 128 : 0;
@@ -102,8 +105,10 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
       const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
       const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
       const int s = ((ci >> 4) << 1) + (rem >> 1);
-      const int mt = col >> 4, c = col & 15, gg = c & 7;
-      const int r = ((rem & 1) << 1) | (c >> 3);
+      // mma row g of an output tile holds channel 2g, row g+8 channel 2g+1 (adjacent channels per
+      // lane: 8-byte weight loads and float2 accumulator updates)
+      const int mt = col >> 4, c = col & 15, gg = c >> 1;
+      const int r = ((rem & 1) << 1) | (c & 1);
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r;
       const float hi = tf32_hi(v);
       Whi[dst] = hi;
@@ -197,6 +202,35 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
 
       // ---- phase 2: uniform loop over dense 8-pair groups ------------------------------------
       float4 G[DEPTH][Q];
+      // direct-weight path: all A fragments of the current offset live in registers, fetched as one
+      // batch of independent loads when the offset changes (one L2 round trip per offset, not per k-step)
+      float wreg[WSMEM ? 1 : KS][WSMEM ? 1 : MT][4];
+      int wreg_k = -1;
+      auto load_w = [&](int kk) {
+        if (WSMEM) return;
+        const int kwt = p.kflip ? (K - 1 - kk) : kk;
+#pragma unroll
+        for (int s = 0; s < (WSMEM ? 1 : KS); ++s) {
+#pragma unroll
+          for (int mt = 0; mt < (WSMEM ? 1 : MT); ++mt) {
+            const float* wp = p.W + (int64_t)kwt * p.w_sk + (int64_t)(16 * (s >> 1) + 4 * t + 2 * (s & 1)) * p.w_si +
+                              (int64_t)(cob + 16 * mt + 2 * g) * p.w_so;
+            if (p.w_so == 1 && w_vec2) {
+              const float2 u0 = __ldg(reinterpret_cast<const float2*>(wp));
+              const float2 u1 = __ldg(reinterpret_cast<const float2*>(wp + p.w_si));
+              wreg[s][mt][0] = u0.x; wreg[s][mt][1] = u0.y; wreg[s][mt][2] = u1.x; wreg[s][mt][3] = u1.y;
+            } else if (p.w_si == 1 && w_vec2) {
+              const float2 u0 = __ldg(reinterpret_cast<const float2*>(wp));
+              const float2 u1 = __ldg(reinterpret_cast<const float2*>(wp + p.w_so));
+              wreg[s][mt][0] = u0.x; wreg[s][mt][2] = u0.y; wreg[s][mt][1] = u1.x; wreg[s][mt][3] = u1.y;
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) wreg[s][mt][r] = __ldg(wp + (r >> 1) * p.w_si + (r & 1) * p.w_so);
+            }
+          }
+        }
+        wreg_k = kk;
+      };
       auto gather = [&](int grp, float4 (&dst)[Q]) {
         const int idx = grp < ng ? in_s[8 * grp + g] : -1;
         const float* src = p.in + (int64_t)(idx >= 0 ? idx : 0) * p.ldi + 4 * t;
@@ -212,6 +246,7 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
           const int grp = g0 + d;
           if (grp < ng) {
             const int kk = gk_s[grp];
+            if (!WSMEM && kk != wreg_k) load_w(kk);
             float dacc[MT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -241,15 +276,12 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
                       al[2] = __float_as_uint(l4.z); al[3] = __float_as_uint(l4.w);
                     }
                   } else {
-                    const int kwt = p.kflip ? (K - 1 - kk) : kk;
-                    const float* wp = p.W + (int64_t)kwt * p.w_sk + (int64_t)(16 * q + 4 * t + 2 * h) * p.w_si +
-                                      (int64_t)(cob + 16 * mt + g) * p.w_so;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                      const float v = __ldg(wp + (int64_t)(r >> 1) * p.w_si + (int64_t)(8 * (r & 1)) * p.w_so);
-                      const float vh = tf32_hi(v);
+                      const float wv = wreg[WSMEM ? 0 : s][WSMEM ? 0 : mt][r];
+                      const float vh = tf32_hi(wv);
                       ah[r] = __float_as_uint(vh);
-                      al[r] = __float_as_uint(v - vh);
+                      al[r] = __float_as_uint(wv - vh);
                     }
                   }
                   if (p.x3) {
@@ -264,14 +296,15 @@ __global__ void __launch_bounds__(NCH == 2 ? 512 : (WSMEM ? 1024 : 288)) k_conv_
             gather(grp + DEPTH, G[d]);
             // D^T fragment -> accumulator rows (padding slots land in the dummy row)
             const int o0 = out_s[8 * grp + 2 * t], o1 = out_s[8 * grp + 2 * t + 1];
-            float* a0 = acc + o0 * AS + g;
-            float* a1 = acc + o1 * AS + g;
+            float2* a0 = reinterpret_cast<float2*>(acc + o0 * AS + 2 * g);
+            float2* a1 = reinterpret_cast<float2*>(acc + o1 * AS + 2 * g);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-              a0[16 * mt] += dacc[mt][0];
-              a0[16 * mt + 8] += dacc[mt][2];
-              a1[16 * mt] += dacc[mt][1];
-              a1[16 * mt + 8] += dacc[mt][3];
+              float2 u = a0[8 * mt], v = a1[8 * mt];
+              u.x += dacc[mt][0]; u.y += dacc[mt][2];
+              v.x += dacc[mt][1]; v.y += dacc[mt][3];
+              a0[8 * mt] = u;
+              a1[8 * mt] = v;
             }
             __syncwarp();
           }
@@ -334,10 +367,22 @@ PPlan plan_pairs(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   if (Cin % 16 || Cout % 16 || Cin > 64 || Cin < 16) return pl;
   pl.Q = Cin / 16;
   const int cot = Cout / 16;
-  pl.MT = cot % 4 == 0 ? 4 : (cot % 3 == 0 ? 3 : (cot % 2 == 0 ? 2 : 1));
   const bool large = n_cap >= 65536;
+  if (large) {
+    // widest output tile whose weights (all K offsets, hi [+ lo]) stay resident next to >= 8 warps
+    pl.MT = 1;
+    for (int mt = 4; mt >= 1; --mt) {
+      if (cot % mt != 0) continue;
+      const int nch = pl.Q * mt > 2 ? 2 : 1;
+      if ((size_t)K * Cin * 16 * mt * 4 * (x3 ? 2 : 1) + 8 * per_warp_bytes(mt, nch) <= (size_t)kMaxSmem) {
+        pl.MT = mt;
+        break;
+      }
+    }
+  } else {
+    pl.MT = (cot % 2 == 0) ? 2 : 1;  // more, smaller tasks when rows are few
+  }
   pl.NCH = (large && pl.Q * pl.MT > 2) ? 2 : 1;
-  if (!large && pl.MT > 2) pl.MT = (cot % 2 == 0) ? 2 : 1;  // more, smaller tasks when rows are few
   pl.passes = cot / pl.MT;
   const size_t pw = per_warp_bytes(pl.MT, pl.NCH);
   const size_t wbytes = (size_t)K * Cin * 16 * pl.MT * 4 * (x3 ? 2 : 1);

@@ -117,6 +117,56 @@ k_conv_rows(const float* __restrict__ in, int64_t ldi, const float* __restrict__
   }
 }
 
+// Stem layer (one input feature, uresnet_sparse.py:21): out[o][c] = sum_k in[tbl[k][o]] * W[k][0][c].
+// Pure bandwidth work: one thread per (row, output channel), the table entry is a warp broadcast.
+__global__ void k_conv_cin1(const float* __restrict__ in, int64_t ldi, const float* __restrict__ W, int64_t w_sk,
+                            int64_t w_so, int kflip, const int32_t* __restrict__ table, int64_t ld, int K,
+                            int64_t n_cap, const int32_t* __restrict__ n_dev, int Cout, float* __restrict__ out,
+                            int64_t ldo) {
+  const int64_t n = live_rows(n_dev, n_cap);
+  const int64_t total = n * Cout;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Cout;
+    const int c = (int)(e - r * Cout);
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int idx = __ldg(table + (int64_t)k * ld + r);
+      if (idx >= 0) acc = fmaf(__ldg(in + (int64_t)idx * ldi), __ldg(W + (int64_t)(kflip ? K - 1 - k : k) * w_sk + c * w_so), acc);
+    }
+    out[r * ldo + c] = acc;
+  }
+}
+
+// Its weight gradient (Ca == 1): dW[k][0][c] = sum_r A[ra] * B[rb][c]; per-chunk partials, folded
+// in chunk order by k_wgrad_reduce.
+__global__ void k_wgrad_ca1(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                            const int32_t* __restrict__ table, int64_t ld, int K, int gather_b, int64_t n_cap,
+                            const int32_t* __restrict__ n_dev, int Cb, int rows_per_split, float* __restrict__ part) {
+  extern __shared__ float red[];  // [RL][Cb]
+  const int n = live_rows(n_dev, n_cap);
+  const int k = blockIdx.x, split = blockIdx.y;
+  const int r_begin = split * rows_per_split;
+  if (r_begin >= n) return;
+  const int r_end = min(n, r_begin + rows_per_split);
+  const int t = threadIdx.x, c = t % Cb, rl = t / Cb, RL = blockDim.x / Cb;
+  float acc = 0.f;
+  if (rl < RL) {
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const int e = table ? __ldg(table + (int64_t)k * ld + r) : r;
+      if (e >= 0) {
+        const int ra = gather_b ? r : e, rb = gather_b ? e : r;
+        acc = fmaf(__ldg(A + (int64_t)ra * lda), __ldg(B + (int64_t)rb * ldb + c), acc);
+      }
+    }
+    red[rl * Cb + c] = acc;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) acc += red[j * Cb + c];
+    part[((int64_t)split * K + k) * Cb + c] = acc;
+  }
+}
+
 template <int NC>
 void launch_rows(int grid, cudaStream_t st, const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si,
                  int64_t w_so, int kflip, const int32_t* table, int64_t ld, const int32_t* parent,
@@ -131,6 +181,15 @@ int conv_rows_dispatch(const float* in, int64_t ldi, const float* W, int64_t w_s
                        int K, int64_t n_cap, const int32_t* n_dev, int Cin, int Cout, float* out, int64_t ldo,
                        int accumulate, cudaStream_t st, const DenseGeom& geom = DenseGeom{}, const float* bias = nullptr) {
   if (n_cap == 0) return 0;
+  if (Cin == 1 && table != nullptr && parent == nullptr && geom.mode == 0 && !accumulate && bias == nullptr) {
+    int64_t g = cdiv(n_cap * Cout, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    k_conv_cin1<<<(int)g, 256, 0, st>>>(in, ldi, W, w_sk, w_so, kflip, table, ld, K, n_cap, n_dev, Cout, out, ldo);
+    count_launches(1);
+    B200_CHECK_LAUNCH("conv_cin1");
+    return 0;
+  }
   int64_t g64 = cdiv(n_cap, kTM);
   const int64_t gmax = (int64_t)sm_count() * 8;
   const int grid = (int)(g64 < gmax ? g64 : gmax);
@@ -263,7 +322,7 @@ __global__ void k_wgrad_reduce(const float* __restrict__ part, int64_t elems, in
 }
 
 void wgrad_plan(int64_t n_cap, int K, int Ca, int Cb, int* nsplit, int* rows_per_split) {
-  int64_t ns = cdiv(n_cap, 2048);
+  int64_t ns = cdiv(n_cap, Ca == 1 ? 256 : 2048);  // the one-input-channel kernel is pure streaming: small chunks
   if (ns < 1) ns = 1;
   if (ns > 128) ns = 128;
   const int64_t per = (int64_t)K * Ca * Cb * 4;
@@ -320,6 +379,11 @@ int wgrad_table_simt(const float* A, int64_t lda, const float* B, int64_t ldb, c
                  (long long)scratch_bytes, (long long)((int64_t)ns * elems * 4));
   const int tiles_a = (Ca + kWT - 1) / kWT, tiles_b = (Cb + kWT - 1) / kWT;
   dim3 grid(K * tiles_a * tiles_b, ns);
+  if (Ca == 1 && Cb <= 256 && geom.mode == 0) {
+    const int RL = 256 / Cb;
+    k_wgrad_ca1<<<dim3(K, ns), RL * Cb, RL * Cb * sizeof(float), st>>>(A, lda, B, ldb, table, ld, K, gather_b, n_cap,
+                                                                      n_dev, Cb, rps, reinterpret_cast<float*>(scratch));
+  } else
   k_wgrad_partial<<<grid, kThreads, 0, st>>>(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, tiles_a,
                                              tiles_b, rps, reinterpret_cast<float*>(scratch), geom);
   int64_t g = cdiv(elems, 256);

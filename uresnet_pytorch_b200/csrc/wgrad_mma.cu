@@ -11,6 +11,8 @@
 // [Ca x Cb] block to scratch.  A second tiny kernel folds the partials in fixed order, so
 // the result is bit-reproducible (no atomics).  Sparse offsets cost what their pair count
 // costs: an offset with 12% valid rows does 12% of the gathers and MMAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200scn {
@@ -34,7 +36,7 @@ struct WgParams {
   int rows_per_cta;
   float* part;
   int x3;
-  float* dW; int accumulate;
+  float* dW; int accumulate; int fused_fold;
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -157,14 +159,16 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
           const float av[4] = {a_row0[mt * 16 + g], a_row0[mt * 16 + g + 8], a_row1[mt * 16 + g],
                                a_row1[mt * 16 + g + 8]};
           const float bx = b_row0[nt * 8 + g], by = b_row1[nt * 8 + g];
+          // hi = truncation to tf32 (one LOP3; cvt.rna expands to ~4 ALU ops), lo = exact remainder
           uint32_t ah[4], al[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) ah[r] = to_tf32(av[r]);
-          const uint32_t b0 = to_tf32(bx), b1 = to_tf32(by);
+          for (int r = 0; r < 4; ++r) ah[r] = __float_as_uint(av[r]) & 0xffffe000u;
+          const uint32_t b0 = __float_as_uint(bx) & 0xffffe000u, b1 = __float_as_uint(by) & 0xffffe000u;
           if (p.x3) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) al[r] = to_tf32(av[r] - __uint_as_float(ah[r]));
-            const uint32_t l0 = to_tf32(bx - __uint_as_float(b0)), l1 = to_tf32(by - __uint_as_float(b1));
+            for (int r = 0; r < 4; ++r) al[r] = __float_as_uint(av[r] - __uint_as_float(ah[r]));
+            const uint32_t l0 = __float_as_uint(bx - __uint_as_float(b0));
+            const uint32_t l1 = __float_as_uint(by - __uint_as_float(b1));
             mma_tf32(acc[i], al, b0, b1);
             mma_tf32(acc[i], ah, l0, l1);
           }
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
     }
   }
 
-  // ---- (5) the last chunk-CTA of this (offset, column split) folds the partial blocks -------------
+  if (!p.fused_fold) return;
+  // ---- (5) optional: the last chunk-CTA of this (offset, column split) folds the partial blocks ----
   __shared__ bool is_last;
   __threadfence();
   __syncthreads();
@@ -205,7 +210,15 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
     const int ci = e / Cbz, co = cb0 + (e - ci * Cbz);
     const int64_t off = (int64_t)ci * p.Cb + co;
     float s = 0.f;
-    for (int c = 0; c < live_chunks; ++c) s += __ldcg(src + c * chunk_stride + off);
+    int c = 0;
+    for (; c + 8 <= live_chunks; c += 8) {  // 8 independent loads in flight, summed in chunk order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (c + u) * chunk_stride + off);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < live_chunks; ++c) s += __ldcg(src + c * chunk_stride + off);
     out[off] = p.accumulate ? out[off] + s : s;
   }
   if (tid == 0) *ticket = 0u;
@@ -246,13 +259,20 @@ WgPlan wg_plan(int64_t n_cap, int K, int Ca, int Cb) {
   z = (Cb + cbz - 1) / cbz;
   const int T = (Ca / 16) * (cbz / 8);
   int warps = T < kWarpsMax ? T : kWarpsMax;
-  if (warps < 2) warps = 2;
+  if (warps < 4) warps = 4;  // extra warps still help the table scan, compaction, gathers and the fold
   int tpw = (T + warps - 1) / warps;
   int tpw_pow = 1;
   while (tpw_pow < tpw) tpw_pow <<= 1;
   if (tpw_pow > 16) return pl;
   // row range per CTA: at most 128 chunks (scratch size, fold cost), at least 256 rows
-  int64_t rows = cdiv(n_cap < 1 ? 1 : n_cap, 128);
+  static int max_chunks = 0;  // tunable for A/B runs: B200SCN_WG_CHUNKS
+  if (max_chunks == 0) {
+    const char* e = getenv("B200SCN_WG_CHUNKS");
+    max_chunks = e ? atoi(e) : 128;
+    if (max_chunks < 1) max_chunks = 1;
+    if (max_chunks > 128) max_chunks = 128;
+  }
+  int64_t rows = cdiv(n_cap < 1 ? 1 : n_cap, max_chunks);
   if (rows < 256) rows = 256;
   rows = cdiv(rows, 256) * 256;
   if (rows > 16384) rows = 16384;  // pair lists live in shared memory
@@ -311,7 +331,12 @@ int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, co
   p.n_cap = n_cap; p.n_dev = n_dev; p.Ca = Ca; p.Cb = Cb; p.cb_per_z = pl.cb_per_z;
   p.rows_per_cta = pl.rows_per_cta; p.part = reinterpret_cast<float*>(scratch);
   p.x3 = (math_mode == B200SCN_MATH_TF32X3) ? 1 : 0;
-  p.dW = dW; p.accumulate = accumulate;
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("B200SCN_WG_FUSED_FOLD");
+    fused = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  p.dW = dW; p.accumulate = accumulate; p.fused_fold = fused;
   B200_CHECK_ARG(K <= 64 && pl.zsplits <= 8, "wgrad_mma: K > 64 or more than 8 column splits");
   int rc = 0;
   switch (pl.tpw) {
@@ -322,7 +347,13 @@ int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, co
     default: rc = wg_launch<16>(p, pl, st); break;
   }
   if (rc) return rc;
-  count_launches(1);
+  if (!p.fused_fold) {
+    int64_t gsz = cdiv(elems, 256);
+    if (gsz > 1024) gsz = 1024;
+    k_wgrad_fold<<<(int)gsz, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), elems, pl.rows_per_cta, pl.nchunks,
+                                           n_cap, n_dev, dW, accumulate);
+  }
+  count_launches(p.fused_fold ? 1 : 2);
   B200_CHECK_LAUNCH("wgrad_mma");
   return 0;
 }
