@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CONFIG = dict(ss=512, uns=5, uf=16, nc=5, dim=3)
+WORKLOAD = "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[1]), Adam, fp32"
 
 
 def parse():
@@ -159,8 +160,7 @@ def run_reference(args):
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d (BASELINE configs[1])"
-                               % args.events_per_gpu},
+        "config": {"workload": WORKLOAD % args.events_per_gpu, "events_per_gpu": args.events_per_gpu},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
                          "sample": "%d full train steps (1 untimed) of the CPU oracle port "
                                    "(scn is not installable here, so the port stands in for the reference's CPU "
@@ -215,8 +215,14 @@ def subm_roofline(args, math_mode):
     # algorithmic bytes: s*(N*Cin + N*Cout) + 4*K*N + s*K*Cin*Cout
     alg = 4 * (n * C + n * C) + 4 * K * n + 4 * K * C * C
     peak, src = peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch, from ncu --set full
+    if os.path.exists(tpath) and args.roofline_events == 128:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("subm16_fwd_bytes_per_launch"), tj.get("source")
     return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
-            "traffic": None, "peak_source": src, "kernel": "b200scn_conv_table (subm 3^3, 16->16, fwd)",
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "kernel": "b200scn_conv_table (subm 3^3, 16->16, fwd)",
             "workload": "%d events of 512^3 concatenated: %d active sites, %d rule pairs (working set > L2)"
                         % (args.roofline_events, n, pairs),
             "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3, "gflops": 2.0 * pairs * C * C / t / 1e9}
@@ -350,8 +356,7 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "f32 (storage and accumulation fp32; products via 3-term tf32 split on mma.sync, fp32-equivalent: tests/test_gpu_mma.py)", "tf32": "tf32 (reduced precision)"}[args.math], "data": "synthetic",
-        "config": {"workload": "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[1]), "
-                               "Adam, fp32" % args.events_per_gpu,
+        "config": {"workload": WORKLOAD % args.events_per_gpu,
                    "events_per_gpu": args.events_per_gpu, "mean_voxels_per_step_per_gpu": vox_all / world / args.steps,
                    "cuda_graph": graph, "row_capacity": cap if graph else None,
                    "l2": "256 MB buffer written between timed steps (L2 flush), outside the CUDA events",
