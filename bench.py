@@ -196,9 +196,17 @@ def subm_roofline(args, math_mode):
     st = torch.cuda.current_stream()
     pairs = int((nbr[:, :n] >= 0).sum().item())
 
+    use_gpl = scn.config.use_gpl and math_mode != scn.MATH_FP32 and not os.environ.get("B200SCN_NO_GPL")
+    gpl = md.subm_gpl(size, 3) if use_gpl else None
+
     def launch():
-        _lib.call("b200scn_conv_table", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, nbr.data_ptr(), nbr.stride(0),
-                  K, n, None, C, C, out.data_ptr(), C, 0, math_mode, st.cuda_stream)
+        if use_gpl:  # what SubmanifoldConvolution.forward runs in the tensor-core math modes
+            _lib.call("b200scn_conv_gpl", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, gpl["tile_off"].data_ptr(),
+                      gpl["g_in"].data_ptr(), gpl["g_meta"].data_ptr(), K, n, None, C, C, out.data_ptr(), C, 0,
+                      math_mode, st.cuda_stream)
+        else:
+            _lib.call("b200scn_conv_table", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, nbr.data_ptr(),
+                      nbr.stride(0), K, n, None, C, C, out.data_ptr(), C, 0, math_mode, st.cuda_stream)
 
     for _ in range(3):
         launch()

@@ -96,3 +96,54 @@ def test_mma_large_batch_against_fp32_kernel():
             c = conv(h).features
     assert (a - b).abs().max().item() <= 2e-5 * a.abs().max().item()
     assert (a - c).abs().max().item() <= 5e-3 * a.abs().max().item()
+
+
+def test_grouped_pair_lists_match_table():
+    """The GPL builder reproduces exactly the (offset, in, out) triples of the neighbour table."""
+    import numpy as np
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+    from helpers import table_as_set
+    data, _ = event_blob(3, 48, dup=20, seed=12)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    md = Metadata(3)
+    size = (48, 48, 48)
+    lv = md.set_input(coords, size)
+    gpl = md.subm_gpl(size, 3)
+    off = gpl["tile_off"].cpu().numpy()
+    g_in = gpl["g_in"].cpu().numpy().reshape(-1, 8)
+    meta = gpl["g_meta"].cpu().numpy().reshape(-1, 4)
+    triples = set()
+    for tile in range(len(off) - 1):
+        ks = []
+        for grp in range(off[tile], off[tile + 1]):
+            k = int(meta[grp, 2])
+            ks.append(k)
+            outs = np.frombuffer(meta[grp, :2].tobytes(), dtype=np.uint8)
+            for s in range(8):
+                if g_in[grp, s] >= 0:
+                    assert outs[s] < 64
+                    triples.add((k, int(g_in[grp, s]), tile * 64 + int(outs[s])))
+                else:
+                    assert outs[s] == 64
+        assert ks == sorted(ks)                     # groups of a tile are ordered by offset
+    assert triples == table_as_set(md.subm_table(size, 3), lv.n)
+    assert off[-1] == len(g_in)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gpl_and_pairs_kernels_agree(mode):
+    """Same layer through the grouped-pair-list kernel and the in-kernel-listing kernel."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    x_o, x_g, f_o, f_g = _pair(3, 24, dup=15)
+    x_o, x_g = _lift(x_o, x_g, f_o, f_g, 32)
+    torch.manual_seed(3)
+    conv = scn.SubmanifoldConvolution(3, 32, 48, 3, False).cuda()
+    with torch.no_grad(), scn.math(mode):
+        a = conv(x_g).features
+        scn.config.use_gpl = False
+        try:
+            b = conv(x_g).features
+        finally:
+            scn.config.use_gpl = True
+    assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()

@@ -350,6 +350,12 @@ inline int grid_for(int64_t n, int block) {
 }
 
 }  // namespace
+
+int scan_i32_public(const int32_t* in, int32_t* out, int64_t n_cap, const int32_t* n_dev, int32_t* total_out,
+                    int32_t* end_out, int32_t* bsums, cudaStream_t st) {
+  return scan_i32(in, out, n_cap, n_dev, total_out, end_out, bsums, st);
+}
+
 }  // namespace b200scn
 
 using namespace b200scn;

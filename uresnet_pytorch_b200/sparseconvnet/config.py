@@ -13,6 +13,10 @@ static_shapes = False
 # before consuming parameter gradients.
 overlap_wgrad = False
 
+# True: tensor-core convolutions read precomputed grouped pair lists (csrc/conv_gpl.cu) instead of
+# re-listing the rule pairs inside every launch (csrc/conv_pairs.cu)
+use_gpl = True
+
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None
 

@@ -76,35 +76,57 @@ def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
     return dW
 
 
+def _gpl_ok(gpl, x, Cin, Cout, math):
+    return (gpl is not None and config.use_gpl and math != 0 and Cin % 16 == 0 and Cout % 16 == 0
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
+
+
+def _conv_gpl(x, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
+    """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
+    K = W3.shape[0]
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), W3.shape[1] * W3.shape[2], w_si, w_so,
+              kflip, gpl["tile_off"].data_ptr(), gpl["g_in"].data_ptr(), gpl["g_meta"].data_ptr(), K, n_out, n_out_dev,
+              Cin, Cout, out.data_ptr(), out.stride(0), 0, math, _stream())
+    return out
+
+
 class TableConv(torch.autograd.Function):
     """out[o] = sum_k x[table[k][o]] @ W[k]; table rows index x.  Used by SubmanifoldConvolution
     (table = neighbour table, symmetric), Convolution (table = child table) and
     NetworkInNetwork (table = None)."""
 
     @staticmethod
-    def forward(ctx, x, W, table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs):
+    def forward(ctx, x, W, table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, gpl_fwd=None,
+                gpl_bwd=None):
         _check_cuda_f32(x, W)
         x = _rowmajor(x)
         W3 = W if W.dim() == 3 else W.unsqueeze(0)
         W3 = W3.contiguous()
         K, Cin, Cout = W3.shape
         math = config.math_mode
-        out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
-        _lib.call("b200scn_conv_table", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1, 0,
-                  _lib.ptr(table), table.stride(0) if table is not None else 0, K, n_out, n_out_dev, Cin, Cout,
-                  out.data_ptr(), out.stride(0), 0, math, _stream())
+        if _gpl_ok(gpl_fwd, x, Cin, Cout, math):
+            out = _conv_gpl(x, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math)
+        else:
+            out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+            _lib.call("b200scn_conv_table", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1, 0,
+                      _lib.ptr(table), table.stride(0) if table is not None else 0, K, n_out, n_out_dev, Cin, Cout,
+                      out.data_ptr(), out.stride(0), 0, math, _stream())
         ctx.save_for_backward(x, W3)
-        ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math)
+        ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math, gpl_bwd)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, W3 = ctx.saved_tensors
-        table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, w_shape, math = ctx.misc
+        table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, w_shape, math, gpl_bwd = ctx.misc
         dout = _rowmajor(dout)
         K, Cin, Cout = W3.shape
         dx = dW = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
+            # same pair structure, transposed weights; the symmetric (submanifold) list needs the offset flip
+            dx = _conv_gpl(dout, W3, 1, Cout, 1 if symmetric else 0, gpl_bwd, n_in, n_in_dev, Cout, Cin, math)
+        elif ctx.needs_input_grad[0]:
             dx = torch.empty((n_in, Cin), dtype=torch.float32, device=x.device)
             if table is None or symmetric:
                 # dx[i] = sum_k dout[table[k][i]] @ W[K-1-k]^T   (neighbour table is symmetric)
@@ -118,35 +140,41 @@ class TableConv(torch.autograd.Function):
                           dx.stride(0), math, _stream())
         if ctx.needs_input_grad[1]:
             dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math)
-        return dx, dW, None, None, None, None, None, None, None, None
+        return dx, dW, None, None, None, None, None, None, None, None, None, None
 
 
 class ParentConv(torch.autograd.Function):
     """out[p] = x[parent[p]] @ W[kofs[p]] (Deconvolution with filter == stride)."""
 
     @staticmethod
-    def forward(ctx, x, W, parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev):
+    def forward(ctx, x, W, parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, gpl_fwd=None,
+                gpl_bwd=None):
         _check_cuda_f32(x, W)
         x = _rowmajor(x)
         W3 = W.contiguous()
         K, Cin, Cout = W3.shape
         math = config.math_mode
-        out = torch.empty((n_fine, Cout), dtype=torch.float32, device=x.device)
-        _lib.call("b200scn_conv_parent", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1,
-                  parent.data_ptr(), kofs.data_ptr(), K, n_fine, n_fine_dev, Cin, Cout, out.data_ptr(), out.stride(0),
-                  math, _stream())
+        if _gpl_ok(gpl_fwd, x, Cin, Cout, math):
+            out = _conv_gpl(x, W3, Cout, 1, 0, gpl_fwd, n_fine, n_fine_dev, Cin, Cout, math)
+        else:
+            out = torch.empty((n_fine, Cout), dtype=torch.float32, device=x.device)
+            _lib.call("b200scn_conv_parent", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1,
+                      parent.data_ptr(), kofs.data_ptr(), K, n_fine, n_fine_dev, Cin, Cout, out.data_ptr(),
+                      out.stride(0), math, _stream())
         ctx.save_for_backward(x, W3)
-        ctx.misc = (parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math)
+        ctx.misc = (parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math, gpl_bwd)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, W3 = ctx.saved_tensors
-        parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math = ctx.misc
+        parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math, gpl_bwd = ctx.misc
         dout = _rowmajor(dout)
         K, Cin, Cout = W3.shape
         dx = dW = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
+            dx = _conv_gpl(dout, W3, 1, Cout, 0, gpl_bwd, n_coarse, n_coarse_dev, Cout, Cin, math)
+        elif ctx.needs_input_grad[0]:
             # dx[j] = sum_k dout[child[k][j]] @ W[k]^T
             dx = torch.empty((n_coarse, Cin), dtype=torch.float32, device=x.device)
             _lib.call("b200scn_conv_table", dout.data_ptr(), dout.stride(0), W3.data_ptr(), Cin * Cout, 1, Cout, 0,
@@ -155,7 +183,7 @@ class ParentConv(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             # dW[k] = sum_j x[j]^T @ dout[child[k][j]]
             dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math)
-        return dx, dW, None, None, None, None, None, None, None
+        return dx, dW, None, None, None, None, None, None, None, None, None
 
 
 class BatchNormAct(torch.autograd.Function):

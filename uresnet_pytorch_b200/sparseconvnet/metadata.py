@@ -27,11 +27,12 @@ def _stream():
 class Level(object):
     """Active sites of one spatial size."""
 
-    __slots__ = ("cap", "n", "n_dev", "ukeys", "tkeys", "tvals", "slots", "subm", "down")
+    __slots__ = ("cap", "n", "n_dev", "ukeys", "tkeys", "tvals", "slots", "subm", "down", "gpl")
 
     def __init__(self):
         self.subm = {}   # filter size -> nbr table int32 [K, cap]
         self.down = {}   # stride -> dict(parent, kofs, child, out_size)
+        self.gpl = {}    # ("subm", k) / ("child", s) / ("parent", s) -> grouped pair list of the rows of this level
 
     @property
     def rows(self):
@@ -162,6 +163,51 @@ class Metadata(object):
         if rules["out_size"] != tuple(out_size):
             raise RuntimeError("inconsistent coarse spatial size")
         return rules
+
+    # -- grouped pair lists (tensor-core convolution input) ------------------------------------
+    def _build_gpl(self, lv, table, parent, kofs, K):
+        """Pair list over the rows of `lv` (the OUTPUT rows of the convolution that will use it)."""
+        L = _lib.load()
+        rows = lv.rows
+        nd = self.n_dev_ptr(lv)
+        tile = L.b200scn_gpl_tile_rows()
+        tiles = max((max(rows, 1) + tile - 1) // tile, 1)
+        dev = self.device
+        tile_off = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        args = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
+                nd, _lib.ptr(tile_off), _lib.ptr(total))
+        _lib.call("b200scn_gpl_build", 0, *args, None, None, 0, _lib.ptr(scratch), nbytes, _stream())
+        if self.static:
+            cap = L.b200scn_gpl_max_groups(max(rows, 1), K)
+        else:
+            cap = max(int(total.item()), 1)
+        g_in = torch.empty(cap * 8, dtype=torch.int32, device=dev)
+        g_meta = torch.empty(cap * 4, dtype=torch.int32, device=dev)
+        _lib.call("b200scn_gpl_build", 1, *args, _lib.ptr(g_in), _lib.ptr(g_meta), cap, _lib.ptr(scratch), nbytes,
+                  _stream())
+        return dict(tile_off=tile_off, g_in=g_in, g_meta=g_meta, K=K)
+
+    def subm_gpl(self, spatial_size, filter_size):
+        lv = self.level(spatial_size)
+        key = ("subm", filter_size)
+        if key not in lv.gpl:
+            nbr = self.subm_table(spatial_size, filter_size)
+            lv.gpl[key] = self._build_gpl(lv, nbr, None, None, filter_size ** self.dimension)
+        return lv.gpl[key]
+
+    def strided_gpl(self, in_size, out_size, stride):
+        """(pair list over the coarse rows from the child table, pair list over the fine rows from parent/kofs)"""
+        rules = self.down_rules(in_size, out_size, stride)
+        fine, coarse = self.level(in_size), self.level(out_size)
+        K = stride ** self.dimension
+        if ("child", stride) not in coarse.gpl:
+            coarse.gpl[("child", stride)] = self._build_gpl(coarse, rules["child"], None, None, K)
+        if ("parent", stride) not in fine.gpl:
+            fine.gpl[("parent", stride)] = self._build_gpl(fine, None, rules["parent"], rules["kofs"], K)
+        return coarse.gpl[("child", stride)], fine.gpl[("parent", stride)]
 
     # -- introspection (tests, debugging) ---------------------------------------------------
     def active_coords(self, spatial_size):

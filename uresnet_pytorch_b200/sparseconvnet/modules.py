@@ -5,6 +5,7 @@ model file runs unchanged with this package imported as `sparseconvnet`.
 """
 import torch
 
+from . import config
 from . import functional as F
 from .metadata import Metadata
 
@@ -179,7 +180,10 @@ class SubmanifoldConvolution(torch.nn.Module):
         lv = md.level(x.spatial_size)
         nbr = md.subm_table(x.spatial_size, self.filter_size)
         nd = md.n_dev_ptr(lv)
-        out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None)
+        gpl = None
+        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+            gpl = md.subm_gpl(x.spatial_size, self.filter_size)
+        out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None, gpl, gpl)
         if self.bias is not None:
             out = out + self.bias
         return x._like(out)
@@ -233,8 +237,11 @@ class Convolution(torch.nn.Module):
         lv = md.level(x.spatial_size)
         rules = md.down_rules(x.spatial_size, out_size, self.s)
         nxt = md.level(out_size)
+        g_child = g_parent = None
+        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+            g_child, g_parent = md.strided_gpl(x.spatial_size, out_size, self.s)
         out = F.TableConv.apply(x.features, self.weight, rules["child"], nxt.rows, md.n_dev_ptr(nxt), lv.rows,
-                                md.n_dev_ptr(lv), False, rules["parent"], rules["kofs"])
+                                md.n_dev_ptr(lv), False, rules["parent"], rules["kofs"], g_child, g_parent)
         if self.bias is not None:
             out = out + self.bias
         return x._like(out, out_size)
@@ -276,8 +283,11 @@ class Deconvolution(torch.nn.Module):
         fine = md.level(out_size)
         rules = md.down_rules(out_size, x.spatial_size, self.s)
         coarse = md.level(x.spatial_size)
+        g_child = g_parent = None
+        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+            g_child, g_parent = md.strided_gpl(out_size, x.spatial_size, self.s)
         out = F.ParentConv.apply(x.features, self.weight, rules["parent"], rules["kofs"], rules["child"], fine.rows,
-                                 md.n_dev_ptr(fine), coarse.rows, md.n_dev_ptr(coarse))
+                                 md.n_dev_ptr(fine), coarse.rows, md.n_dev_ptr(coarse), g_parent, g_child)
         if self.bias is not None:
             out = out + self.bias
         return x._like(out, out_size)
