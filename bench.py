@@ -230,7 +230,7 @@ def subm_roofline(args, math_mode):
             tj = json.load(f)
         traffic, traffic_src = tj.get("subm16_fwd_bytes_per_launch"), tj.get("source")
     return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "kernel": "b200scn_conv_table (subm 3^3, 16->16, fwd)",
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "kernel": ("b200scn_conv_gpl" if use_gpl else "b200scn_conv_table") + " (subm 3^3, 16->16, fwd)",
             "workload": "%d events of 512^3 concatenated: %d active sites, %d rule pairs (working set > L2)"
                         % (args.roofline_events, n, pairs),
             "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3, "gflops": 2.0 * pairs * C * C / t / 1e9}

@@ -14,6 +14,17 @@ from test_gpu_layers import _check, _lift, _pair
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=[0, 1 << 30], ids=["gpl", "pairs"])
+def _conv_path(request):
+    """Run every test of this file through both tensor-core conv paths: grouped pair lists for all levels
+    (threshold 0) and in-kernel listing only (threshold huge)."""
+    from uresnet_pytorch_b200.sparseconvnet import config
+    prev = config.gpl_min_rows
+    config.gpl_min_rows = request.param
+    yield
+    config.gpl_min_rows = prev
+
 TOL = {1: (3e-5, 2e-4), 2: (5e-3, 1e-2)}  # math mode -> (forward, gradient)
 
 
@@ -121,11 +132,10 @@ def test_grouped_pair_lists_match_table():
             ks.append(k)
             outs = np.frombuffer(meta[grp, :2].tobytes(), dtype=np.uint8)
             for s in range(8):
-                if g_in[grp, s] >= 0:
-                    assert outs[s] < 64
+                if outs[s] < 64:
                     triples.add((k, int(g_in[grp, s]), tile * 64 + int(outs[s])))
                 else:
-                    assert outs[s] == 64
+                    assert outs[s] == 64 and g_in[grp, s] == 0   # padding: dummy output row
         assert ks == sorted(ks)                     # groups of a tile are ordered by offset
     assert triples == table_as_set(md.subm_table(size, 3), lv.n)
     assert off[-1] == len(g_in)

@@ -6,7 +6,7 @@
 // done ONCE per level by the rulebook builder and kept in HBM:
 //     tile      = 64 consecutive output rows
 //     group     = 8 rule pairs of one kernel offset inside one tile (last group of an offset padded)
-//     g_in  [G][8] int32   input row of every pair (-1 = padding)
+//     g_in  [G][8] int32   input row of every pair (padding slots: row 0, routed to a dummy output row)
 //     g_meta[G]    int4    {out rows 0..3, out rows 4..7 (local, 1 byte each; 64 = dummy), offset k, 0}
 //     tile_off[T+1] int32  group range of every tile (groups sorted by offset inside a tile)
 // 48 B per group, ~2.3 groups per site-offset... in practice ~0.9 groups per site at the finest
@@ -17,6 +17,8 @@
 // read-modify-write into a per-warp shared accumulator -> one coalesced store per output row.
 // Large inputs: one warp per tile, weights resident in shared memory.  Small inputs: one tile per
 // CTA, its warps split the tile's groups and their partial accumulators are summed in warp order.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200scn {
@@ -92,7 +94,7 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
         const int pad = ng * 8 - cnt;
         if (lane < pad) {
           const int s = cnt + lane;
-          gin[s] = -1;
+          gin[s] = 0;  // any valid row: the slot's products only ever reach the dummy accumulator row
           gout[(s >> 3) * 16 + (s & 7)] = (unsigned char)kTileRows;  // dummy accumulator row
         }
         if (lane < ng) {
@@ -119,7 +121,7 @@ struct GplParams {
   int warps, split;  // split != 0: the CTA's warps share one tile
 };
 
-template <int Q, int MT, bool WSMEM>
+template <int Q, int MT, bool WSMEM, bool X3>
 __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(const GplParams p) {
   constexpr int R = kTileRows, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
   constexpr int DEPTH = Q == 1 ? 4 : 2;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
   float* Whi = reinterpret_cast<float*>(smem_raw);
   float* Wlo = Whi + w_elems;
   constexpr int kAccBytes = (R + 1) * AS * 4;
-  const int warp_off = w_elems * 4 * (p.x3 ? 2 : 1) + warp * kAccBytes;
+  const int warp_off = w_elems * 4 * (X3 ? 2 : 1) + warp * kAccBytes;
   float* const acc = reinterpret_cast<float*>(smem_raw + warp_off);
   const bool w_vec2 = ((reinterpret_cast<uintptr_t>(p.W) & 7) == 0) && (p.w_sk % 2 == 0) &&
                       (p.w_si % 2 == 0 || p.w_si == 1) && (p.w_so % 2 == 0 || p.w_so == 1);
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r;
       const float hi = tf32_hi(v);
       Whi[dst] = hi;
-      if (p.x3) Wlo[dst] = v - hi;
+      if (X3) Wlo[dst] = v - hi;
     }
     __syncthreads();
   }
@@ -184,20 +186,35 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
     }
     __syncwarp();
 
+    // two-level prefetch: group records (row index, meta) travel 2*DEPTH groups ahead of the MMAs,
+    // the feature rows they point to DEPTH groups ahead -- neither load sits on the critical path
     float4 G[DEPTH][Q];
-    int4 M[DEPTH];
-    auto fetch = [&](int grp, int d) {
-      int idx = -1;
-      if (grp < ge) {
-        idx = __ldg(p.g_in + (int64_t)grp * 8 + g);
-        M[d] = __ldg(p.g_meta + grp);
-      }
-      const float* src = p.in + (int64_t)(idx >= 0 ? idx : 0) * p.ldi + 4 * t;
-#pragma unroll
-      for (int q = 0; q < Q; ++q) G[d][q] = idx >= 0 ? __ldg(reinterpret_cast<const float4*>(src + 16 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 M[DEPTH], Mn[DEPTH];
+    int In[DEPTH];
+    // (records and rows past the end of the range are clamped to the last group: redundant but
+    // unconditional loads, never consumed)
+    const int g_last = max(ge - 1, gb);
+    const int32_t* gin_l = p.g_in + g;
+    const float4* in_l = reinterpret_cast<const float4*>(p.in + 4 * t);
+    const int ld4 = p.ldi >> 2;  // row stride in float4 (ldi % 4 == 0)
+    auto fetch_rec = [&](int grp, int d) {
+      const int gc = min(grp, g_last);
+      In[d] = __ldg(gin_l + (int64_t)gc * 8);
+      Mn[d] = __ldg(p.g_meta + gc);
     };
+    auto fetch = [&](int grp, int d) {
+      const float4* src = in_l + (int64_t)In[d] * ld4;
+      M[d] = Mn[d];
 #pragma unroll
-    for (int d = 0; d < DEPTH; ++d) fetch(gb + d, d);
+      for (int q = 0; q < Q; ++q) G[d][q] = __ldg(src + 4 * q);
+      fetch_rec(grp + DEPTH, d);
+    };
+    if (gb < ge) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) fetch_rec(gb + d, d);
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) fetch(gb + d, d);
+    }
 
     float wreg[WSMEM ? 1 : KS][WSMEM ? 1 : MT][4];
     int wreg_k = -1;
@@ -233,6 +250,7 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
             }
             wreg_k = kk;
           }
+          const int wk_off = kk * (KS * MT * 128) + lane * 4;
           float dacc[MT][4];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
@@ -245,18 +263,19 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
             for (int h = 0; h < 2; ++h) {
               const int s = 2 * q + h;
               const float bx = bv[2 * h], by = bv[2 * h + 1];
-              const float bxh = tf32_hi(bx), byh = tf32_hi(by);
+              // single-pass tf32: raw fp32 bits (the tensor core ignores the low mantissa bits)
+              const float bxh = X3 ? tf32_hi(bx) : bx, byh = X3 ? tf32_hi(by) : by;
               const uint32_t b0 = __float_as_uint(bxh), b1 = __float_as_uint(byh);
               const uint32_t l0 = __float_as_uint(bx - bxh), l1 = __float_as_uint(by - byh);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 uint32_t ah[4], al[4];
                 if (WSMEM) {
-                  const int off = (((kk * KS + s) * MT + mt) * 32 + lane) * 4;
+                  const int off = wk_off + (s * MT + mt) * 128;
                   const float4 a4 = *reinterpret_cast<const float4*>(Whi + off);
                   ah[0] = __float_as_uint(a4.x); ah[1] = __float_as_uint(a4.y);
                   ah[2] = __float_as_uint(a4.z); ah[3] = __float_as_uint(a4.w);
-                  if (p.x3) {
+                  if (X3) {
                     const float4 l4 = *reinterpret_cast<const float4*>(Wlo + off);
                     al[0] = __float_as_uint(l4.x); al[1] = __float_as_uint(l4.y);
                     al[2] = __float_as_uint(l4.z); al[3] = __float_as_uint(l4.w);
@@ -265,12 +284,12 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
 #pragma unroll
                   for (int r = 0; r < 4; ++r) {
                     const float wv = wreg[WSMEM ? 0 : s][WSMEM ? 0 : mt][r];
-                    const float vh = tf32_hi(wv);
+                    const float vh = X3 ? tf32_hi(wv) : wv;
                     ah[r] = __float_as_uint(vh);
                     al[r] = __float_as_uint(wv - vh);
                   }
                 }
-                if (p.x3) {
+                if (X3) {
                   mma_tf32(dacc[mt], al, b0, b1);
                   mma_tf32(dacc[mt], ah, l0, l1);
                 }
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
     if (split) __syncthreads();
     const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const int e_begin = split ? tid : lane, e_step = split ? (int)blockDim.x : 32;
-    const float* acc0 = reinterpret_cast<const float*>(smem_raw + w_elems * 4 * (p.x3 ? 2 : 1));
+    const float* acc0 = reinterpret_cast<const float*>(smem_raw + w_elems * 4 * (X3 ? 2 : 1));
     for (int e = e_begin; e < R * (CT / 4); e += e_step) {
       const int row = e / (CT / 4), c4 = e - row * (CT / 4);
       if (base + row < n) {
@@ -363,7 +382,13 @@ GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   pl.wsmem = large && (wbytes + 8 * acc_bytes(pl.MT) <= (size_t)kMaxSmem);
   pl.split = large ? 0 : 1;
   const size_t fixed = pl.wsmem ? wbytes : 0;
-  int warps = large ? 24 : 8;
+  static int large_warps = 0;  // B200SCN_GPL_WARPS: warps per CTA of the large-input variant (A/B runs)
+  if (large_warps == 0) {
+    const char* e = getenv("B200SCN_GPL_WARPS");
+    large_warps = e ? atoi(e) : 24;
+    if (large_warps < 1 || large_warps > 24) large_warps = 24;
+  }
+  int warps = large ? large_warps : 8;
   while (warps > 1 && fixed + warps * acc_bytes(pl.MT) > (size_t)kMaxSmem) --warps;
   if (fixed + warps * acc_bytes(pl.MT) > (size_t)kMaxSmem) return pl;
   if (!pl.wsmem && warps > 8) warps = 8;  // launch bound of the direct-weight variant
@@ -378,11 +403,11 @@ GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   return pl;
 }
 
-template <int Q, int MT, bool WSMEM>
+template <int Q, int MT, bool WSMEM, bool X3>
 int launch_gpl(const GplParams& p, const GPlan& pl, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, WSMEM, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
   const int64_t tiles = cdiv(p.n_cap, kTileRows);
@@ -392,7 +417,7 @@ int launch_gpl(const GplParams& p, const GPlan& pl, cudaStream_t st) {
   if (gx > gmax) gx = gmax;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)pl.passes);
-  k_conv_gpl<Q, MT, WSMEM><<<grid, pl.warps * 32, pl.smem, st>>>(p);
+  k_conv_gpl<Q, MT, WSMEM, X3><<<grid, pl.warps * 32, pl.smem, st>>>(p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
@@ -400,8 +425,8 @@ int launch_gpl(const GplParams& p, const GPlan& pl, cudaStream_t st) {
 
 template <int Q, int MT>
 int launch_gpl_qm(const GplParams& p, const GPlan& pl, cudaStream_t st) {
-  if (pl.wsmem) return launch_gpl<Q, MT, true>(p, pl, st);
-  return launch_gpl<Q, MT, false>(p, pl, st);
+  if (pl.wsmem) return p.x3 ? launch_gpl<Q, MT, true, true>(p, pl, st) : launch_gpl<Q, MT, true, false>(p, pl, st);
+  return p.x3 ? launch_gpl<Q, MT, false, true>(p, pl, st) : launch_gpl<Q, MT, false, false>(p, pl, st);
 }
 
 template <int Q>

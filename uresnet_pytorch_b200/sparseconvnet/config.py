@@ -1,5 +1,6 @@
 """Process-wide switches of the b200 sparseconvnet surface."""
 import contextlib
+import os
 
 # B200SCN_MATH_* of include/b200scn.h: 0 = fp32 FFMA, 1 = tf32x3 tensor-core (fp32-equivalent), 2 = tf32
 MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
@@ -15,7 +16,10 @@ overlap_wgrad = False
 
 # True: tensor-core convolutions read precomputed grouped pair lists (csrc/conv_gpl.cu) instead of
 # re-listing the rule pairs inside every launch (csrc/conv_pairs.cu)
-use_gpl = True
+use_gpl = not os.environ.get("B200SCN_NO_GPL")
+# levels with fewer rows keep the in-kernel listing (conv_pairs.cu, offset-split CTAs): building the lists
+# costs more than it saves when one launch is a few microseconds
+gpl_min_rows = int(os.environ.get("B200SCN_GPL_MIN_ROWS", "65536"))
 
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None

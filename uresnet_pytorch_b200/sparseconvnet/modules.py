@@ -181,7 +181,8 @@ class SubmanifoldConvolution(torch.nn.Module):
         nbr = md.subm_table(x.spatial_size, self.filter_size)
         nd = md.n_dev_ptr(lv)
         gpl = None
-        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+        if (config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0
+                and lv.rows >= config.gpl_min_rows):
             gpl = md.subm_gpl(x.spatial_size, self.filter_size)
         out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None, gpl, gpl)
         if self.bias is not None:
@@ -238,7 +239,8 @@ class Convolution(torch.nn.Module):
         rules = md.down_rules(x.spatial_size, out_size, self.s)
         nxt = md.level(out_size)
         g_child = g_parent = None
-        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+        if (config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0
+                and nxt.rows >= config.gpl_min_rows):
             g_child, g_parent = md.strided_gpl(x.spatial_size, out_size, self.s)
         out = F.TableConv.apply(x.features, self.weight, rules["child"], nxt.rows, md.n_dev_ptr(nxt), lv.rows,
                                 md.n_dev_ptr(lv), False, rules["parent"], rules["kofs"], g_child, g_parent)
@@ -284,7 +286,8 @@ class Deconvolution(torch.nn.Module):
         rules = md.down_rules(out_size, x.spatial_size, self.s)
         coarse = md.level(x.spatial_size)
         g_child = g_parent = None
-        if config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0:
+        if (config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0
+                and coarse.rows >= config.gpl_min_rows):
             g_child, g_parent = md.strided_gpl(out_size, x.spatial_size, self.s)
         out = F.ParentConv.apply(x.features, self.weight, rules["parent"], rules["kofs"], rules["child"], fine.rows,
                                  md.n_dev_ptr(fine), coarse.rows, md.n_dev_ptr(coarse), g_parent, g_child)
