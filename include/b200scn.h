@@ -99,17 +99,19 @@ int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_de
                        void* stream);
 
 /* Grouped pair lists (GPL): the rulebook of one (level, layer type) in the form the tensor-core
- * convolution consumes -- per 64-row output tile, the rule pairs of every offset packed into
- * groups of 8 (csrc/conv_gpl.cu).  Built once per level, shared by every forward / dgrad use.
+ * convolution consumes -- per tile of `tile_rows` (64 or 128) output rows, the rule pairs of every offset
+ * packed into groups of 16 (csrc/conv_gpl.cu).  Built once per level, shared by every forward / dgrad use.
  * Source of the pairs: `table` (offset-major, as above), or parent/kofs (Deconvolution-style:
  * pair (parent[p] -> p) at offset kofs[p]), or neither (identity, K == 1).
- * stage 0 -> tile_off[tiles + 1], total_dev[1];  stage 1 -> g_in[8 * cap_groups], g_meta[16 B * cap_groups]. */
-int b200scn_gpl_tile_rows(void);
-int64_t b200scn_gpl_max_groups(int64_t n_cap, int K);
+ * Record format: g_rec[group][8] int4; entry j = { in row of pair j, in row of pair j+8,
+ * out(j) | out(j+8) << 8 | k << 16, 0 } with out = row inside the tile (tile_rows = padding slot).
+ * stage 0 -> tile_off[tiles + 1], total_dev[1];  stage 1 -> g_rec[128 B * cap_groups]. */
+int b200scn_gpl_tile_rows(int64_t n_cap); /* recommended tile_rows for a level of n_cap rows */
+int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows);
 int64_t b200scn_gpl_scratch_bytes(int64_t n_cap);
 int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs, int K,
-                      int64_t n_cap, const int32_t* n_dev, int32_t* tile_off, int32_t* total_dev, int32_t* g_in,
-                      void* g_meta, int64_t cap_groups, void* scratch, int64_t scratch_bytes, void* stream);
+                      int64_t n_cap, const int32_t* n_dev, int tile_rows, int32_t* tile_off, int32_t* total_dev,
+                      void* g_rec, int64_t cap_groups, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (ii) gather-GEMM(-scatter) convolutions -- SubmanifoldConvolution / Convolution /
@@ -126,7 +128,7 @@ int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_s
 
 /* the same contraction driven by a grouped pair list (tensor-core math modes, channels % 16 == 0) */
 int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so, int kflip,
-                     const int32_t* tile_off, const int32_t* g_in, const void* g_meta, int K, int64_t n_out_cap,
+                     int tile_rows, const int32_t* tile_off, const void* g_rec, int K, int64_t n_out_cap,
                      const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
                      int math_mode, void* stream);
 

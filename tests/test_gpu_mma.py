@@ -109,7 +109,8 @@ def test_mma_large_batch_against_fp32_kernel():
     assert (a - c).abs().max().item() <= 5e-3 * a.abs().max().item()
 
 
-def test_grouped_pair_lists_match_table():
+@pytest.mark.parametrize("tile_rows", [64, 128])
+def test_grouped_pair_lists_match_table(tile_rows, monkeypatch):
     """The GPL builder reproduces exactly the (offset, in, out) triples of the neighbour table."""
     import numpy as np
     from uresnet_pytorch_b200 import sparseconvnet as scn
@@ -117,28 +118,34 @@ def test_grouped_pair_lists_match_table():
     from helpers import table_as_set
     data, _ = event_blob(3, 48, dup=20, seed=12)
     coords = torch.from_numpy(data[:, :4]).cuda()
+    monkeypatch.setattr(scn.config, "gpl_tile_rows", tile_rows)
     md = Metadata(3)
     size = (48, 48, 48)
     lv = md.set_input(coords, size)
     gpl = md.subm_gpl(size, 3)
     off = gpl["tile_off"].cpu().numpy()
-    g_in = gpl["g_in"].cpu().numpy().reshape(-1, 8)
-    meta = gpl["g_meta"].cpu().numpy().reshape(-1, 4)
+    R = gpl["tile_rows"]
+    rec = gpl["g_rec"].cpu().numpy().reshape(-1, 8, 4)   # [group][entry j][in(j), in(j+8), out bytes | k, 0]
     triples = set()
     for tile in range(len(off) - 1):
         ks = []
         for grp in range(off[tile], off[tile + 1]):
-            k = int(meta[grp, 2])
-            ks.append(k)
-            outs = np.frombuffer(meta[grp, :2].tobytes(), dtype=np.uint8)
-            for s in range(8):
-                if outs[s] < 64:
-                    triples.add((k, int(g_in[grp, s]), tile * 64 + int(outs[s])))
-                else:
-                    assert outs[s] == 64 and g_in[grp, s] == 0   # padding: dummy output row
+            kset = set()
+            for j in range(8):
+                word = int(rec[grp, j, 2]) & 0xFFFFFFFF
+                kset.add((word >> 16) & 0xFF)
+                assert rec[grp, j, 3] == 0 and (word >> 24) == 0
+                for half in range(2):
+                    o = (word >> (8 * half)) & 0xFF
+                    if o < R:
+                        triples.add(((word >> 16) & 0xFF, int(rec[grp, j, half]), tile * R + o))
+                    else:
+                        assert o == R and rec[grp, j, half] == 0   # padding: dummy output row
+            assert len(kset) == 1                   # one offset per group
+            ks.append(kset.pop())
         assert ks == sorted(ks)                     # groups of a tile are ordered by offset
     assert triples == table_as_set(md.subm_table(size, 3), lv.n)
-    assert off[-1] == len(g_in)
+    assert off[-1] == len(rec)
 
 
 @pytest.mark.parametrize("mode", [1, 2])

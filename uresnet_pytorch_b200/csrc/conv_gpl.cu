@@ -1,22 +1,31 @@
-// Grouped pair lists (GPL): the rulebook in the form the tensor-core convolution consumes.
+// Grouped pair lists (GPL): the rulebook in the form the tensor-core convolution consumes, and the
+// convolution kernel over them.
 //
-// profiles/README.md section 2: in k_conv_pairs a third of the issue slots go to listing the rule
-// pairs of every (32-row tile, offset) -- work that depends only on the rulebook and is redone by
-// each of the ~16 forward/dgrad uses of a U-Net level per training step.  Here that listing is
-// done ONCE per level by the rulebook builder and kept in HBM:
-//     tile      = 64 consecutive output rows
-//     group     = 8 rule pairs of one kernel offset inside one tile (last group of an offset padded)
-//     g_in  [G][8] int32   input row of every pair (padding slots: row 0, routed to a dummy output row)
-//     g_meta[G]    int4    {out rows 0..3, out rows 4..7 (local, 1 byte each; 64 = dummy), offset k, 0}
-//     tile_off[T+1] int32  group range of every tile (groups sorted by offset inside a tile)
-// 48 B per group, ~2.3 groups per site-offset... in practice ~0.9 groups per site at the finest
-// level: ~45 B/site instead of the 108 B/site neighbour table.
+// profiles/README.md section 2: listing the rule pairs of every (tile, offset) inside the conv kernel
+// cost a third of its issue slots -- work that depends only on the rulebook and is redone by each of
+// the ~16 forward/dgrad uses of a U-Net level per training step.  Here the listing is done ONCE per
+// level by the rulebook builder and kept in HBM:
+//     tile      = R consecutive output rows (R = 128, or 64 for levels with few rows)
+//     group     = 16 rule pairs of one kernel offset inside one tile (last group of an offset padded)
+//     g_rec[G][8] int4   entry j of a group describes its pairs j and j+8:
+//                        { in row (j), in row (j+8), out(j) | out(j+8) << 8 | k << 16, 0 }
+//                        (out = row inside the tile, R = dummy row of a padding slot, whose in row is 0)
+//     tile_off[T+1] int32  group range of every tile (groups of a tile are sorted by offset)
+// 128 B per group, ~0.35 groups per site at the finest level: ~45 B/site instead of the 108 B/site
+// neighbour table, and one LDG.128 per lane hands the kernel everything it needs to know about a group.
 //
-// k_conv_gpl then is only the dense inner loop: prefetched group records -> LDG.128 row gathers
-// straight into the mma B fragment -> mma.sync m16n8k8 tf32 (optionally 3-term split) -> float2
-// read-modify-write into a per-warp shared accumulator -> one coalesced store per output row.
-// Large inputs: one warp per tile, weights resident in shared memory.  Small inputs: one tile per
-// CTA, its warps split the tile's groups and their partial accumulators are summed in warp order.
+// k_conv_gpl is then only the dense inner loop.  One mma.sync m16n8k8 tf32 per (16 pairs, 8 input
+// channels, 8 output channels): the PAIRS are the M dimension, so
+//   A = gathered feature rows, LDG.128 straight into the fragment (lane (g,t) loads channels 4t..4t+3
+//       of the rows of pairs g and g+8; the k index of the MMA is a permutation of the channels),
+//   B = W[k], pre-arranged in fragment order in shared memory (large inputs) or read from L1/L2,
+//   C = the current value of the 16 output rows in a per-warp shared-memory accumulator, D goes back
+//       to the same place: the scatter-add costs one LDS.128 + one STS.128 per row and no FADD.
+// Within one offset every output row occurs once, and a warp walks its groups in order, so the
+// accumulation order is fixed: offsets ascending, exactly like the reference's rulebook loop.
+// tf32x3 (fp32-equivalent): D = C + A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// Large inputs: one warp per tile, 20 warps per SM.  Small inputs: one tile per CTA, its warps split
+// the tile's groups and their partial accumulators are summed in warp order.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,79 +37,80 @@ int scan_i32_public(const int32_t* in, int32_t* out, int64_t n_cap, const int32_
 
 namespace {
 
-constexpr int kTileRows = 64;
 constexpr int kMaxSmem = 220 * 1024;
+constexpr int kLargeWarps = 20;
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+// D(16 pairs x 8 co) += A(16 pairs x 8 ci) * B(8 ci x 8 co)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 // ---- builder -------------------------------------------------------------------------------------
 // one warp per tile; FILL == false: count groups per tile; FILL == true: write the records
-template <bool FILL>
+template <bool FILL, int R>
 __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const int32_t* __restrict__ parent,
                             const uint8_t* __restrict__ kofs, int K, int64_t n_cap, const int32_t* __restrict__ n_dev,
                             int32_t* __restrict__ tile_cnt, const int32_t* __restrict__ tile_off,
-                            int32_t* __restrict__ g_in, int4* __restrict__ g_meta, int64_t cap_groups) {
+                            int4* __restrict__ g_rec, int64_t cap_groups) {
+  constexpr int NR = R / 32;  // rows per lane
   const int n = live_rows(n_dev, n_cap);
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  const int64_t n_tiles = ((int64_t)n + kTileRows - 1) / kTileRows;
+  const int64_t n_tiles = ((int64_t)n + R - 1) / R;
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (int64_t tile = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); tile < n_tiles;
        tile += (int64_t)gridDim.x * warps) {
-    const int base = (int)(tile * kTileRows);
-    const int r0 = base + lane, r1 = base + 32 + lane;
-    int pk0 = -1, pk1 = -1, pp0 = -1, pp1 = -1;
-    if (parent != nullptr) {
-      if (r0 < n) { pk0 = kofs[r0]; pp0 = __ldg(parent + r0); }
-      if (r1 < n) { pk1 = kofs[r1]; pp1 = __ldg(parent + r1); }
+    const int base = (int)(tile * R);
+    int pk[NR], pp[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      pk[i] = -1; pp[i] = -1;
+      const int r = base + 32 * i + lane;
+      if (parent != nullptr && r < n) { pk[i] = kofs[r]; pp[i] = __ldg(parent + r); }
     }
     int64_t grp = FILL ? (int64_t)tile_off[tile] : 0;
     int count = 0;
     for (int k = 0; k < K; ++k) {
-      int e0 = -1, e1 = -1;
-      if (parent != nullptr) {
-        e0 = pk0 == k ? pp0 : -1;
-        e1 = pk1 == k ? pp1 : -1;
-      } else if (table != nullptr) {
-        if (r0 < n) e0 = __ldg(table + (int64_t)k * ld + r0);
-        if (r1 < n) e1 = __ldg(table + (int64_t)k * ld + r1);
-      } else {
-        if (r0 < n) e0 = r0;
-        if (r1 < n) e1 = r1;
+      int e[NR], pre[NR];
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int r = base + 32 * i + lane;
+        e[i] = -1;
+        if (parent != nullptr) {
+          e[i] = pk[i] == k ? pp[i] : -1;
+        } else if (table != nullptr) {
+          if (r < n) e[i] = __ldg(table + (int64_t)k * ld + r);
+        } else {
+          if (r < n) e[i] = r;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, e[i] >= 0);
+        pre[i] = cnt + __popc(m & lt_mask);
+        cnt += __popc(m);
       }
-      const uint32_t m0 = __ballot_sync(0xffffffffu, e0 >= 0), m1 = __ballot_sync(0xffffffffu, e1 >= 0);
-      const int c0 = __popc(m0), cnt = c0 + __popc(m1);
-      const int ng = (cnt + 7) >> 3;
+      const int ng = (cnt + 15) >> 4;
       if (FILL && ng > 0 && grp + ng <= cap_groups) {
-        // slot of this lane's pairs inside the offset's padded block of ng*8 slots
-        int32_t* gin = g_in + grp * 8;
-        unsigned char* gout = reinterpret_cast<unsigned char*>(g_meta + grp);  // 16 B per group: 8 out bytes first
-        if (e0 >= 0) {
-          const int s = __popc(m0 & lt_mask);
-          gin[s] = e0;
-          gout[(s >> 3) * 16 + (s & 7)] = (unsigned char)lane;
-        }
-        if (e1 >= 0) {
-          const int s = c0 + __popc(m1 & lt_mask);
-          gin[s] = e1;
-          gout[(s >> 3) * 16 + (s & 7)] = (unsigned char)(32 + lane);
-        }
-        const int pad = ng * 8 - cnt;
-        if (lane < pad) {
-          const int s = cnt + lane;
-          gin[s] = 0;  // any valid row: the slot's products only ever reach the dummy accumulator row
-          gout[(s >> 3) * 16 + (s & 7)] = (unsigned char)kTileRows;  // dummy accumulator row
-        }
-        if (lane < ng) {
-          int* meta = reinterpret_cast<int*>(g_meta + grp + lane);
-          meta[2] = k;
-          meta[3] = 0;
+        int32_t* rec = reinterpret_cast<int32_t*>(g_rec + grp * 8);
+        auto put = [&](int s, int in_row, int out_row) {
+          const int w = s & 15;
+          int32_t* ent = rec + ((s >> 4) * 8 + (w & 7)) * 4;
+          ent[w >> 3] = in_row;
+          reinterpret_cast<unsigned char*>(ent + 2)[w >> 3] = (unsigned char)out_row;
+        };
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+          if (e[i] >= 0) put(pre[i], e[i], 32 * i + lane);
+        // padding slots: any valid input row, routed to the dummy accumulator row
+        if (lane < ng * 16 - cnt) put(cnt + lane, 0, R);
+        for (int j = lane; j < ng * 8; j += 32) {
+          unsigned char* b = reinterpret_cast<unsigned char*>(rec + j * 4 + 2);
+          b[2] = (unsigned char)k;
+          b[3] = 0;
+          rec[j * 4 + 3] = 0;
         }
       }
       grp += ng;
@@ -114,17 +124,20 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
 struct GplParams {
   const float* in; int ldi;
   const float* W; int w_sk, w_si, w_so; int kflip;
-  const int32_t* tile_off; const int32_t* g_in; const int4* g_meta;
+  const int32_t* tile_off; const int4* g_rec;
   int K;
   int64_t n_cap; const int32_t* n_dev;
-  float* out; int ldo; int accumulate; int x3;
+  float* out; int ldo; int accumulate;
   int warps, split;  // split != 0: the CTA's warps share one tile
 };
 
-template <int Q, int MT, bool WSMEM, bool X3>
-__global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(const GplParams p) {
-  constexpr int R = kTileRows, KS = 2 * Q, CT = 16 * MT, AS = CT + 8;
-  constexpr int DEPTH = Q == 1 ? 4 : 2;
+// Q = Cin / 16, MT = output channels of this pass / 16, WSMEM: all K weight slices resident in shared
+// memory in fragment order, X3: 3-term tf32 split, R: tile rows.
+template <int Q, int MT, bool WSMEM, bool X3, int R>
+__global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(const GplParams p) {
+  constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4;
+  constexpr int DEPTH = Q == 1 ? 3 : (Q == 2 ? 2 : 1);
+  constexpr bool SWZ = (MT % 2) == 0;  // row stride is a multiple of 128 B: alternate rows swap 64 B halves
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
@@ -138,13 +151,13 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
   const int w_elems = WSMEM ? K * KS * MT * 128 : 0;
   float* Whi = reinterpret_cast<float*>(smem_raw);
   float* Wlo = Whi + w_elems;
-  constexpr int kAccBytes = (R + 1) * AS * 4;
-  const int warp_off = w_elems * 4 * (X3 ? 2 : 1) + warp * kAccBytes;
-  float* const acc = reinterpret_cast<float*>(smem_raw + warp_off);
-  const bool w_vec2 = ((reinterpret_cast<uintptr_t>(p.W) & 7) == 0) && (p.w_sk % 2 == 0) &&
-                      (p.w_si % 2 == 0 || p.w_si == 1) && (p.w_so % 2 == 0 || p.w_so == 1);
+  constexpr int kAccBytes = (R + 1) * CT * 4;
+  const int acc_base = w_elems * 4 * (X3 ? 2 : 1);
+  float4* const acc = reinterpret_cast<float4*>(smem_raw + acc_base + warp * kAccBytes);
 
   if (WSMEM) {
+    // fragment order: [(k, kstep s, mt)][lane][4] = {b0, b1 of the even n-tile, b0, b1 of the odd n-tile}
+    // b0/b1 = W[ci = 16q + 4t + 2h (+1)][co], co = 16 mt + 4 (g >> 1) + 2 * odd + (g & 1)
     const bool co_fast = (p.w_so == 1);
     const int fast_n = co_fast ? CT : 16 * Q, slow_n = co_fast ? 16 * Q : CT;
     const int total = K * slow_n * fast_n;
@@ -158,9 +171,9 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
       const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
       const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
       const int s = ((ci >> 4) << 1) + (rem >> 1);
-      const int mt = col >> 4, c = col & 15, gg = c >> 1;
-      const int r = ((rem & 1) << 1) | (c & 1);
-      const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + r;
+      const int mt = col >> 4, c = col & 15;
+      const int gg = ((c >> 2) << 1) | (c & 1), odd = (c >> 1) & 1;
+      const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + odd * 2 + (rem & 1);
       const float hi = tf32_hi(v);
       Whi[dst] = hi;
       if (X3) Wlo[dst] = v - hi;
@@ -174,8 +187,7 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
   for (int64_t wt = wt0; wt < n_tiles; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
-    for (int e = lane; e < (R + 1) * AS / 4; e += 32)
-      reinterpret_cast<float4*>(acc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     // this warp's group range
     int gb = __ldg(p.tile_off + wt), ge = __ldg(p.tile_off + wt + 1);
     if (split) {
@@ -186,27 +198,25 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
     }
     __syncwarp();
 
-    // two-level prefetch: group records (row index, meta) travel 2*DEPTH groups ahead of the MMAs,
-    // the feature rows they point to DEPTH groups ahead -- neither load sits on the critical path
-    float4 G[DEPTH][Q];
+    // two-level prefetch: group records travel 2*DEPTH groups ahead of the MMAs, the feature rows they
+    // point to DEPTH groups ahead.  Records and rows past the end of the range are clamped to the last
+    // group: redundant but unconditional loads, never consumed.
+    float4 G[DEPTH][2][Q];
     int4 M[DEPTH], Mn[DEPTH];
-    int In[DEPTH];
-    // (records and rows past the end of the range are clamped to the last group: redundant but
-    // unconditional loads, never consumed)
     const int g_last = max(ge - 1, gb);
-    const int32_t* gin_l = p.g_in + g;
-    const float4* in_l = reinterpret_cast<const float4*>(p.in + 4 * t);
+    const int4* rec_l = p.g_rec + g;
+    const float4* in_l = reinterpret_cast<const float4*>(p.in) + t;
     const int ld4 = p.ldi >> 2;  // row stride in float4 (ldi % 4 == 0)
-    auto fetch_rec = [&](int grp, int d) {
-      const int gc = min(grp, g_last);
-      In[d] = __ldg(gin_l + (int64_t)gc * 8);
-      Mn[d] = __ldg(p.g_meta + gc);
-    };
+    auto fetch_rec = [&](int grp, int d) { Mn[d] = __ldg(rec_l + (int64_t)min(grp, g_last) * 8); };
     auto fetch = [&](int grp, int d) {
-      const float4* src = in_l + (int64_t)In[d] * ld4;
       M[d] = Mn[d];
+      const float4* s0 = in_l + (int64_t)M[d].x * ld4;
+      const float4* s1 = in_l + (int64_t)M[d].y * ld4;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) G[d][q] = __ldg(src + 4 * q);
+      for (int q = 0; q < Q; ++q) {
+        G[d][0][q] = __ldg(s0 + 4 * q);
+        G[d][1][q] = __ldg(s1 + 4 * q);
+      }
       fetch_rec(grp + DEPTH, d);
     };
     if (gb < ge) {
@@ -216,100 +226,93 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
       for (int d = 0; d < DEPTH; ++d) fetch(gb + d, d);
     }
 
-    float wreg[WSMEM ? 1 : KS][WSMEM ? 1 : MT][4];
-    int wreg_k = -1;
-
     for (int g0 = gb; g0 < ge; g0 += DEPTH) {
 #pragma unroll
       for (int d = 0; d < DEPTH; ++d) {
         const int grp = g0 + d;
         if (grp < ge) {
-          const int kk = M[d].z;
-          const uint32_t o_lo = (uint32_t)M[d].x, o_hi = (uint32_t)M[d].y;
-          if (!WSMEM && kk != wreg_k) {
-            const int kwt = p.kflip ? (K - 1 - kk) : kk;
+          const uint32_t mz = (uint32_t)M[d].z;
+          const int kk = (mz >> 16) & 0xff;
+          const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
+          float4* const r0 = acc + o0 * C4;
+          float4* const r1 = acc + o1 * C4;
+          const int x0 = SWZ ? ((o0 & 1) << 2) : 0, x1 = SWZ ? ((o1 & 1) << 2) : 0;
+          // C operand: the rows' running sums (n-tile 2mt holds channels 4t, 4t+1 of 16-channel block mt,
+          // n-tile 2mt+1 holds 4t+2, 4t+3)
+          float dacc[MT][2][4];
 #pragma unroll
-            for (int s = 0; s < (WSMEM ? 1 : KS); ++s) {
-#pragma unroll
-              for (int mt = 0; mt < (WSMEM ? 1 : MT); ++mt) {
-                const float* wp = p.W + (int64_t)kwt * p.w_sk + (int64_t)(16 * (s >> 1) + 4 * t + 2 * (s & 1)) * p.w_si +
-                                  (int64_t)(cob + 16 * mt + 2 * g) * p.w_so;
-                if (p.w_so == 1 && w_vec2) {
-                  const float2 u0 = __ldg(reinterpret_cast<const float2*>(wp));
-                  const float2 u1 = __ldg(reinterpret_cast<const float2*>(wp + p.w_si));
-                  wreg[s][mt][0] = u0.x; wreg[s][mt][1] = u0.y; wreg[s][mt][2] = u1.x; wreg[s][mt][3] = u1.y;
-                } else if (p.w_si == 1 && w_vec2) {
-                  const float2 u0 = __ldg(reinterpret_cast<const float2*>(wp));
-                  const float2 u1 = __ldg(reinterpret_cast<const float2*>(wp + p.w_so));
-                  wreg[s][mt][0] = u0.x; wreg[s][mt][2] = u0.y; wreg[s][mt][1] = u1.x; wreg[s][mt][3] = u1.y;
-                } else {
-#pragma unroll
-                  for (int r = 0; r < 4; ++r) wreg[s][mt][r] = __ldg(wp + (r >> 1) * p.w_si + (r & 1) * p.w_so);
-                }
-              }
-            }
-            wreg_k = kk;
+          for (int mt = 0; mt < MT; ++mt) {
+            const float4 v0 = r0[(4 * mt + t) ^ x0], v1 = r1[(4 * mt + t) ^ x1];
+            dacc[mt][0][0] = v0.x; dacc[mt][0][1] = v0.y; dacc[mt][0][2] = v1.x; dacc[mt][0][3] = v1.y;
+            dacc[mt][1][0] = v0.z; dacc[mt][1][1] = v0.w; dacc[mt][1][2] = v1.z; dacc[mt][1][3] = v1.w;
           }
+          const int kwt = p.kflip ? (K - 1 - kk) : kk;
+          const float* wk = WSMEM ? nullptr : p.W + (int64_t)kwt * p.w_sk + (int64_t)(4 * t) * p.w_si +
+                                                  (int64_t)(cob + 4 * (g >> 1) + (g & 1)) * p.w_so;
           const int wk_off = kk * (KS * MT * 128) + lane * 4;
-          float dacc[MT][4];
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) dacc[mt][r] = 0.f;
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            const float bv[4] = {G[d][q].x, G[d][q].y, G[d][q].z, G[d][q].w};
+            const float f0[4] = {G[d][0][q].x, G[d][0][q].y, G[d][0][q].z, G[d][0][q].w};
+            const float f1[4] = {G[d][1][q].x, G[d][1][q].y, G[d][1][q].z, G[d][1][q].w};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int s = 2 * q + h;
-              const float bx = bv[2 * h], by = bv[2 * h + 1];
-              // single-pass tf32: raw fp32 bits (the tensor core ignores the low mantissa bits)
-              const float bxh = X3 ? tf32_hi(bx) : bx, byh = X3 ? tf32_hi(by) : by;
-              const uint32_t b0 = __float_as_uint(bxh), b1 = __float_as_uint(byh);
-              const uint32_t l0 = __float_as_uint(bx - bxh), l1 = __float_as_uint(by - byh);
+              // a0 = (pair g, ci 4t+2h), a1 = (pair g+8, same ci), a2 = (pair g, ci+1), a3 = (pair g+8, ci+1)
+              const float av[4] = {f0[2 * h], f1[2 * h], f0[2 * h + 1], f1[2 * h + 1]};
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                // single-pass tf32: raw fp32 bits (the tensor core ignores the low mantissa bits)
+                const float hi = X3 ? tf32_hi(av[r]) : av[r];
+                ah[r] = __float_as_uint(hi);
+                al[r] = __float_as_uint(av[r] - hi);
+              }
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
-                uint32_t ah[4], al[4];
+                float w4[4];
                 if (WSMEM) {
-                  const int off = wk_off + (s * MT + mt) * 128;
-                  const float4 a4 = *reinterpret_cast<const float4*>(Whi + off);
-                  ah[0] = __float_as_uint(a4.x); ah[1] = __float_as_uint(a4.y);
-                  ah[2] = __float_as_uint(a4.z); ah[3] = __float_as_uint(a4.w);
+                  const float4 b4 = *reinterpret_cast<const float4*>(Whi + wk_off + (s * MT + mt) * 128);
+                  w4[0] = b4.x; w4[1] = b4.y; w4[2] = b4.z; w4[3] = b4.w;
+                } else {
+                  const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
+                  w4[0] = __ldg(wp);
+                  w4[1] = __ldg(wp + p.w_si);
+                  w4[2] = __ldg(wp + 2 * p.w_so);
+                  w4[3] = __ldg(wp + p.w_si + 2 * p.w_so);
+                }
+                uint32_t bh[2][2], bl[2][2];
+                if (WSMEM) {
+#pragma unroll
+                  for (int r = 0; r < 4; ++r) bh[r >> 1][r & 1] = __float_as_uint(w4[r]);
                   if (X3) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(Wlo + off);
-                    al[0] = __float_as_uint(l4.x); al[1] = __float_as_uint(l4.y);
-                    al[2] = __float_as_uint(l4.z); al[3] = __float_as_uint(l4.w);
+                    const float4 l4 = *reinterpret_cast<const float4*>(Wlo + wk_off + (s * MT + mt) * 128);
+                    bl[0][0] = __float_as_uint(l4.x); bl[0][1] = __float_as_uint(l4.y);
+                    bl[1][0] = __float_as_uint(l4.z); bl[1][1] = __float_as_uint(l4.w);
                   }
                 } else {
 #pragma unroll
                   for (int r = 0; r < 4; ++r) {
-                    const float wv = wreg[WSMEM ? 0 : s][WSMEM ? 0 : mt][r];
-                    const float vh = X3 ? tf32_hi(wv) : wv;
-                    ah[r] = __float_as_uint(vh);
-                    al[r] = __float_as_uint(wv - vh);
+                    const float hi = X3 ? tf32_hi(w4[r]) : w4[r];
+                    bh[r >> 1][r & 1] = __float_as_uint(hi);
+                    bl[r >> 1][r & 1] = __float_as_uint(w4[r] - hi);
                   }
                 }
-                if (X3) {
-                  mma_tf32(dacc[mt], al, b0, b1);
-                  mma_tf32(dacc[mt], ah, l0, l1);
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                  if (X3) {
+                    mma_tf32(dacc[mt][o], al, bh[o]);
+                    mma_tf32(dacc[mt][o], ah, bl[o]);
+                  }
+                  mma_tf32(dacc[mt][o], ah, bh[o]);
                 }
-                mma_tf32(dacc[mt], ah, b0, b1);
               }
             }
           }
           fetch(grp + DEPTH, d);  // this slot is free again
-          // pairs 2t and 2t+1 of the group -> accumulator rows (padding lands in the dummy row)
-          const uint32_t ow = t < 2 ? o_lo : o_hi;
-          const int o0 = (ow >> (16 * (t & 1))) & 0xff, o1 = (ow >> (16 * (t & 1) + 8)) & 0xff;
-          float2* a0 = reinterpret_cast<float2*>(acc + o0 * AS + 2 * g);
-          float2* a1 = reinterpret_cast<float2*>(acc + o1 * AS + 2 * g);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            float2 u = a0[8 * mt], v = a1[8 * mt];
-            u.x += dacc[mt][0]; u.y += dacc[mt][2];
-            v.x += dacc[mt][1]; v.y += dacc[mt][3];
-            a0[8 * mt] = u;
-            a1[8 * mt] = v;
+            r0[(4 * mt + t) ^ x0] = make_float4(dacc[mt][0][0], dacc[mt][0][1], dacc[mt][1][0], dacc[mt][1][1]);
+            r1[(4 * mt + t) ^ x1] = make_float4(dacc[mt][0][2], dacc[mt][0][3], dacc[mt][1][2], dacc[mt][1][3]);
           }
           __syncwarp();
         }
@@ -320,19 +323,20 @@ __global__ void __launch_bounds__(WSMEM ? 768 : 256, WSMEM ? 1 : 2) k_conv_gpl(c
     if (split) __syncthreads();
     const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const int e_begin = split ? tid : lane, e_step = split ? (int)blockDim.x : 32;
-    const float* acc0 = reinterpret_cast<const float*>(smem_raw + w_elems * 4 * (X3 ? 2 : 1));
-    for (int e = e_begin; e < R * (CT / 4); e += e_step) {
-      const int row = e / (CT / 4), c4 = e - row * (CT / 4);
+    const float4* acc0 = reinterpret_cast<const float4*>(smem_raw + acc_base);
+    for (int e = e_begin; e < R * C4; e += e_step) {
+      const int row = e / C4, c4 = e - row * C4;
       if (base + row < n) {
+        const int src = row * C4 + (c4 ^ (SWZ ? ((row & 1) << 2) : 0));
         float4 v;
         if (split) {
           v = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int w = 0; w < warps; ++w) {
-            const float4 u = *reinterpret_cast<const float4*>(acc0 + w * (kAccBytes / 4) + row * AS + 4 * c4);
+            const float4 u = acc0[w * (kAccBytes / 16) + src];
             v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
           }
         } else {
-          v = *reinterpret_cast<const float4*>(acc + row * AS + 4 * c4);
+          v = acc[src];
         }
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
         if (vec_ok) {
@@ -357,43 +361,46 @@ struct GPlan {
   size_t smem;
 };
 
-GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3) {
+size_t acc_bytes(int R, int mt) { return (size_t)(R + 1) * (16 * mt) * 4; }
+
+GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3, int R) {
   GPlan pl{};
   pl.ok = false;
   if (Cin % 16 || Cout % 16 || Cin > 64 || Cin < 16) return pl;
   pl.Q = Cin / 16;
   const int cot = Cout / 16;
-  const bool large = n_cap >= 65536;
-  auto acc_bytes = [](int mt) { return (size_t)(kTileRows + 1) * (16 * mt + 8) * 4; };
+  // large: enough tiles to give every SM a CTA full of one-tile warps
+  const bool large = R == 128 && n_cap >= (int64_t)R * 8 * sm_count();
+  pl.MT = 1;
   if (large) {
-    pl.MT = 1;
-    for (int mt = 4; mt >= 1; --mt) {
+    for (int mt = 2; mt >= 1; --mt) {
       if (cot % mt != 0) continue;
-      if ((size_t)K * Cin * 16 * mt * 4 * (x3 ? 2 : 1) + 8 * acc_bytes(mt) <= (size_t)kMaxSmem) {
+      if ((size_t)K * Cin * 16 * mt * 4 * (x3 ? 2 : 1) + 12 * acc_bytes(R, mt) <= (size_t)kMaxSmem) {
         pl.MT = mt;
         break;
       }
     }
   } else {
-    pl.MT = (cot % 2 == 0) ? 2 : 1;
+    // small inputs: narrow passes until the grid covers the SMs
+    const int64_t tiles = cdiv(n_cap, R);
+    pl.MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
   }
   pl.passes = cot / pl.MT;
   const size_t wbytes = (size_t)K * Cin * 16 * pl.MT * 4 * (x3 ? 2 : 1);
-  pl.wsmem = large && (wbytes + 8 * acc_bytes(pl.MT) <= (size_t)kMaxSmem);
+  pl.wsmem = large && (wbytes + 12 * acc_bytes(R, pl.MT) <= (size_t)kMaxSmem);
   pl.split = large ? 0 : 1;
   const size_t fixed = pl.wsmem ? wbytes : 0;
   static int large_warps = 0;  // B200SCN_GPL_WARPS: warps per CTA of the large-input variant (A/B runs)
   if (large_warps == 0) {
     const char* e = getenv("B200SCN_GPL_WARPS");
-    large_warps = e ? atoi(e) : 24;
-    if (large_warps < 1 || large_warps > 24) large_warps = 24;
+    large_warps = e ? atoi(e) : kLargeWarps;
+    if (large_warps < 1 || large_warps > kLargeWarps) large_warps = kLargeWarps;
   }
-  int warps = large ? large_warps : 8;
-  while (warps > 1 && fixed + warps * acc_bytes(pl.MT) > (size_t)kMaxSmem) --warps;
-  if (fixed + warps * acc_bytes(pl.MT) > (size_t)kMaxSmem) return pl;
-  if (!pl.wsmem && warps > 8) warps = 8;  // launch bound of the direct-weight variant
+  int warps = pl.wsmem ? large_warps : 8;
+  while (warps > 1 && fixed + warps * acc_bytes(R, pl.MT) > (size_t)kMaxSmem) --warps;
+  if (fixed + warps * acc_bytes(R, pl.MT) > (size_t)kMaxSmem) return pl;
   pl.warps = warps;
-  pl.smem = fixed + warps * acc_bytes(pl.MT);
+  pl.smem = fixed + warps * acc_bytes(R, pl.MT);
   int cps = (int)((size_t)(227 * 1024) / (pl.smem + 1024));
   if (cps > 2048 / (warps * 32)) cps = 2048 / (warps * 32);
   if (cps > 8) cps = 8;
@@ -403,40 +410,37 @@ GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3) {
   return pl;
 }
 
-template <int Q, int MT, bool WSMEM, bool X3>
+template <int Q, int MT, bool WSMEM, bool X3, int R>
 int launch_gpl(const GplParams& p, const GPlan& pl, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, WSMEM, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, WSMEM, X3, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kMaxSmem));
     configured = true;
   }
-  const int64_t tiles = cdiv(p.n_cap, kTileRows);
+  const int64_t tiles = cdiv(p.n_cap, R);
   int64_t gx = pl.split ? tiles : cdiv(tiles, pl.warps);
   int64_t gmax = WSMEM ? ((int64_t)sm_count() * pl.ctas_per_sm) / pl.passes : (int64_t)sm_count() * pl.ctas_per_sm * 4;
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)pl.passes);
-  k_conv_gpl<Q, MT, WSMEM, X3><<<grid, pl.warps * 32, pl.smem, st>>>(p);
+  k_conv_gpl<Q, MT, WSMEM, X3, R><<<grid, pl.warps * 32, pl.smem, st>>>(p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
 }
 
-template <int Q, int MT>
-int launch_gpl_qm(const GplParams& p, const GPlan& pl, cudaStream_t st) {
-  if (pl.wsmem) return p.x3 ? launch_gpl<Q, MT, true, true>(p, pl, st) : launch_gpl<Q, MT, true, false>(p, pl, st);
-  return p.x3 ? launch_gpl<Q, MT, false, true>(p, pl, st) : launch_gpl<Q, MT, false, false>(p, pl, st);
+template <int Q, int MT, bool X3>
+int launch_gpl_qmx(const GplParams& p, const GPlan& pl, int R, cudaStream_t st) {
+  if (pl.wsmem) return launch_gpl<Q, MT, true, X3, 128>(p, pl, st);
+  return R == 128 ? launch_gpl<Q, MT, false, X3, 128>(p, pl, st) : launch_gpl<Q, MT, false, X3, 64>(p, pl, st);
 }
 
 template <int Q>
-int launch_gpl_q(const GplParams& p, const GPlan& pl, cudaStream_t st) {
-  switch (pl.MT) {
-    case 1: return launch_gpl_qm<Q, 1>(p, pl, st);
-    case 2: return launch_gpl_qm<Q, 2>(p, pl, st);
-    case 3: return launch_gpl_qm<Q, 3>(p, pl, st);
-    default: return launch_gpl_qm<Q, 4>(p, pl, st);
-  }
+int launch_gpl_q(const GplParams& p, const GPlan& pl, int R, int x3, cudaStream_t st) {
+  if (pl.MT == 1) return x3 ? launch_gpl_qmx<Q, 1, true>(p, pl, R, st) : launch_gpl_qmx<Q, 1, false>(p, pl, R, st);
+  return x3 ? launch_gpl_qmx<Q, 2, true>(p, pl, R, st) : launch_gpl_qmx<Q, 2, false>(p, pl, R, st);
 }
 
 }  // namespace
@@ -444,48 +448,61 @@ int launch_gpl_q(const GplParams& p, const GPlan& pl, cudaStream_t st) {
 
 using namespace b200scn;
 
-extern "C" int b200scn_gpl_tile_rows(void) { return kTileRows; }
+/* tile rows the library recommends for a level of n_cap rows */
+extern "C" int b200scn_gpl_tile_rows(int64_t n_cap) { return n_cap >= 12288 ? 128 : 64; }
 
 /* upper bound of the number of groups for n_cap rows (static regime allocation) */
-extern "C" int64_t b200scn_gpl_max_groups(int64_t n_cap, int K) {
-  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, kTileRows);
-  return tiles * (int64_t)K * (kTileRows / 8);
+extern "C" int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows) {
+  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
+  return tiles * (int64_t)K * (tile_rows / 16);
 }
 
 extern "C" int64_t b200scn_gpl_scratch_bytes(int64_t n_cap) {
-  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, kTileRows);
+  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, 64);
   return (tiles + 8) * 4 + (cdiv(tiles, 1024) + 16) * 4 + 256;
 }
 
 /* stage 0: tile_off[tiles + 1] (exclusive scan of the per-tile group counts) and total_dev[1].
- * stage 1: fill g_in[cap_groups * 8] / g_meta[cap_groups] (int4 records) using tile_off. */
+ * stage 1: fill g_rec[cap_groups * 8] (int4 records) using tile_off. */
 extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent,
-                                 const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int32_t* tile_off,
-                                 int32_t* total_dev, int32_t* g_in, void* g_meta, int64_t cap_groups, void* scratch,
+                                 const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int tile_rows,
+                                 int32_t* tile_off, int32_t* total_dev, void* g_rec, int64_t cap_groups, void* scratch,
                                  int64_t scratch_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= 64, "gpl_build: K must be 1..64");
+  B200_CHECK_ARG(tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 64 or 128");
   B200_CHECK_ARG(scratch_bytes >= b200scn_gpl_scratch_bytes(n_cap), "gpl_build: scratch too small");
-  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, kTileRows);
+  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(scratch);
   int32_t* bsums = tile_cnt + tiles + 8;
-  const int warps = 8;
+  const int warps = 4;
   int64_t grid = cdiv(tiles, warps);
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * 16;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  int4* rec = reinterpret_cast<int4*>(g_rec);
   if (stage == 0) {
     B200_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(tiles + 8) * 4, st));
-    if (n_cap > 0)
-      k_gpl_build<false><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, nullptr,
-                                                           nullptr, nullptr, 0);
+    if (n_cap > 0) {
+      if (tile_rows == 128)
+        k_gpl_build<false, 128><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
+                                                                  nullptr, nullptr, 0);
+      else
+        k_gpl_build<false, 64><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
+                                                                 nullptr, nullptr, 0);
+    }
     // exclusive scan over all `tiles` counts (tiles beyond the live ones hold 0)
     if (int rc = scan_i32_public(tile_cnt, tile_off, tiles, nullptr, total_dev, tile_off, bsums, st)) return rc;
     count_launches(4);
   } else {
-    if (n_cap > 0)
-      k_gpl_build<true><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, nullptr, tile_off,
-                                                          g_in, reinterpret_cast<int4*>(g_meta), cap_groups);
+    if (n_cap > 0) {
+      if (tile_rows == 128)
+        k_gpl_build<true, 128><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
+                                                                 tile_off, rec, cap_groups);
+      else
+        k_gpl_build<true, 64><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
+                                                                tile_off, rec, cap_groups);
+    }
     count_launches(1);
   }
   B200_CHECK_LAUNCH("gpl_build");
@@ -493,32 +510,33 @@ extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, co
 }
 
 extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
-                                int kflip, const int32_t* tile_off, const int32_t* g_in, const void* g_meta, int K,
+                                int kflip, int tile_rows, const int32_t* tile_off, const void* g_rec, int K,
                                 int64_t n_out_cap, const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo,
                                 int accumulate, int math_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16, "conv_gpl: channels must be multiples of 16");
   B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "conv_gpl: tensor-core math modes only");
   B200_CHECK_ARG(ldi % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv_gpl: input rows must be 16-byte aligned");
+  B200_CHECK_ARG(tile_rows == 64 || tile_rows == 128, "conv_gpl: tile_rows must be 64 or 128");
   const int64_t lim = (1ll << 31) - 1;
   B200_CHECK_ARG(ldi < lim && ldo < lim && (int64_t)K * Cin * Cout < lim, "conv_gpl: stride out of 32-bit range");
   if (n_out_cap == 0) return 0;
   const int x3 = math_mode == B200SCN_MATH_TF32X3 ? 1 : 0;
   for (int c0 = 0; c0 < Cin; c0 += 64) {
     const int cc = Cin - c0 < 64 ? Cin - c0 : 64;
-    GPlan pl = plan_gpl(K, cc, Cout, n_out_cap, x3);
+    GPlan pl = plan_gpl(K, cc, Cout, n_out_cap, x3, tile_rows);
     B200_CHECK_ARG(pl.ok, "conv_gpl: unsupported shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
     GplParams p;
     p.in = in + c0; p.ldi = (int)ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = (int)w_sk; p.w_si = (int)w_si;
-    p.w_so = (int)w_so; p.kflip = kflip; p.tile_off = tile_off; p.g_in = g_in;
-    p.g_meta = reinterpret_cast<const int4*>(g_meta); p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out;
-    p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.x3 = x3; p.warps = pl.warps; p.split = pl.split;
+    p.w_so = (int)w_so; p.kflip = kflip; p.tile_off = tile_off; p.g_rec = reinterpret_cast<const int4*>(g_rec);
+    p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out;
+    p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.warps = pl.warps; p.split = pl.split;
     int rc;
     switch (pl.Q) {
-      case 1: rc = launch_gpl_q<1>(p, pl, st); break;
-      case 2: rc = launch_gpl_q<2>(p, pl, st); break;
-      case 3: rc = launch_gpl_q<3>(p, pl, st); break;
-      default: rc = launch_gpl_q<4>(p, pl, st); break;
+      case 1: rc = launch_gpl_q<1>(p, pl, tile_rows, x3, st); break;
+      case 2: rc = launch_gpl_q<2>(p, pl, tile_rows, x3, st); break;
+      case 3: rc = launch_gpl_q<3>(p, pl, tile_rows, x3, st); break;
+      default: rc = launch_gpl_q<4>(p, pl, tile_rows, x3, st); break;
     }
     if (rc) return rc;
   }

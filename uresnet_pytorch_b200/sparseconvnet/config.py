@@ -21,6 +21,9 @@ use_gpl = not os.environ.get("B200SCN_NO_GPL")
 # costs more than it saves when one launch is a few microseconds
 gpl_min_rows = int(os.environ.get("B200SCN_GPL_MIN_ROWS", "65536"))
 
+# rows per tile of the grouped pair lists (64 / 128); None = the library's recommendation for the level size
+gpl_tile_rows = int(os.environ["B200SCN_GPL_TILE_ROWS"]) if os.environ.get("B200SCN_GPL_TILE_ROWS") else None
+
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None
 

@@ -86,7 +86,7 @@ def _conv_gpl(x, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), W3.shape[1] * W3.shape[2], w_si, w_so,
-              kflip, gpl["tile_off"].data_ptr(), gpl["g_in"].data_ptr(), gpl["g_meta"].data_ptr(), K, n_out, n_out_dev,
+              kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), gpl["g_rec"].data_ptr(), K, n_out, n_out_dev,
               Cin, Cout, out.data_ptr(), out.stride(0), 0, math, _stream())
     return out
 

@@ -170,7 +170,7 @@ class Metadata(object):
         L = _lib.load()
         rows = lv.rows
         nd = self.n_dev_ptr(lv)
-        tile = L.b200scn_gpl_tile_rows()
+        tile = config.gpl_tile_rows or L.b200scn_gpl_tile_rows(max(rows, 1))
         tiles = max((max(rows, 1) + tile - 1) // tile, 1)
         dev = self.device
         tile_off = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
@@ -178,17 +178,15 @@ class Metadata(object):
         nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         args = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
-                nd, _lib.ptr(tile_off), _lib.ptr(total))
-        _lib.call("b200scn_gpl_build", 0, *args, None, None, 0, _lib.ptr(scratch), nbytes, _stream())
+                nd, tile, _lib.ptr(tile_off), _lib.ptr(total))
+        _lib.call("b200scn_gpl_build", 0, *args, None, 0, _lib.ptr(scratch), nbytes, _stream())
         if self.static:
-            cap = L.b200scn_gpl_max_groups(max(rows, 1), K)
+            cap = L.b200scn_gpl_max_groups(max(rows, 1), K, tile)
         else:
             cap = max(int(total.item()), 1)
-        g_in = torch.empty(cap * 8, dtype=torch.int32, device=dev)
-        g_meta = torch.empty(cap * 4, dtype=torch.int32, device=dev)
-        _lib.call("b200scn_gpl_build", 1, *args, _lib.ptr(g_in), _lib.ptr(g_meta), cap, _lib.ptr(scratch), nbytes,
-                  _stream())
-        return dict(tile_off=tile_off, g_in=g_in, g_meta=g_meta, K=K)
+        g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)  # [cap][8] int4 records
+        _lib.call("b200scn_gpl_build", 1, *args, _lib.ptr(g_rec), cap, _lib.ptr(scratch), nbytes, _stream())
+        return dict(tile_off=tile_off, g_rec=g_rec, K=K, tile_rows=tile)
 
     def subm_gpl(self, spatial_size, filter_size):
         lv = self.level(spatial_size)
