@@ -129,15 +129,45 @@ struct GplParams {
   int64_t n_cap; const int32_t* n_dev;
   float* out; int ldo; int accumulate;
   int warps, split;  // split != 0: the CTA's warps share one tile
+  uint32_t ones;     // 0xffffffff (opaque to the compiler)
 };
+
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// one 32-bit word of a group record.  Scalar on purpose: a vector load pins its destination to an aligned
+// register quad, and ptxas then copies the fields out of it right behind the load -- a stall for the
+// full memory latency on every group
+__device__ __forceinline__ int ldg_nc32(const void* ptr) {
+  int v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
 
 // Q = Cin / 16, MT = output channels of this pass / 16, WSMEM: all K weight slices resident in shared
 // memory in fragment order, X3: 3-term tf32 split, R: tile rows.
+//
+// Fragment <-> channel maps (lane = 4 g + t):
+//   A (k-step s = 2q + h): a0/a1 = pair g / g+8 at ci = 16q + 4t + 2h, a2/a3 = same pairs at ci + 1
+//   B (n-tile j):          b0 = W[16q + 4t + 2h][8j + g], b1 = W[16q + 4t + 2h + 1][8j + g]
+//   C/D (n-tile j):        d0,d1 = pair g, co = 8j + 2t, 8j + 2t + 1;  d2,d3 = pair g+8, same co
+// Accumulator row r keeps its 8-channel chunk j at position j ^ x(r), x(r) = (r >> 1) & 1 (MT odd) or
+// r & 3 (MT even), so that the LDS.64/STS.64 of four consecutive rows fall into distinct banks.
 template <int Q, int MT, bool WSMEM, bool X3, int R>
 __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(const GplParams p) {
-  constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4;
-  constexpr int DEPTH = Q == 1 ? 3 : (Q == 2 ? 2 : 1);
-  constexpr bool SWZ = (MT % 2) == 0;  // row stride is a multiple of 128 B: alternate rows swap 64 B halves
+  constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
+  constexpr int DEPTH = Q == 1 ? 2 : 1;  // feature rows are fetched DEPTH groups ahead, records 2*DEPTH
+  constexpr int RING = 2 * DEPTH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
@@ -154,10 +184,12 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   constexpr int kAccBytes = (R + 1) * CT * 4;
   const int acc_base = w_elems * 4 * (X3 ? 2 : 1);
   float4* const acc = reinterpret_cast<float4*>(smem_raw + acc_base + warp * kAccBytes);
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t s_acc = s_base + acc_base + warp * kAccBytes + t * 8;  // + row * CT * 4 + chunk * 32
+  const uint32_t s_whi = s_base + lane * 16, s_wlo = s_whi + w_elems * 4;
 
   if (WSMEM) {
-    // fragment order: [(k, kstep s, mt)][lane][4] = {b0, b1 of the even n-tile, b0, b1 of the odd n-tile}
-    // b0/b1 = W[ci = 16q + 4t + 2h (+1)][co], co = 16 mt + 4 (g >> 1) + 2 * odd + (g & 1)
+    // fragment order: [(k, kstep s, mt)][lane][4] = {b0, b1 of n-tile 2mt, b0, b1 of n-tile 2mt+1}
     const bool co_fast = (p.w_so == 1);
     const int fast_n = co_fast ? CT : 16 * Q, slow_n = co_fast ? 16 * Q : CT;
     const int total = K * slow_n * fast_n;
@@ -171,8 +203,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
       const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
       const int s = ((ci >> 4) << 1) + (rem >> 1);
-      const int mt = col >> 4, c = col & 15;
-      const int gg = ((c >> 2) << 1) | (c & 1), odd = (c >> 1) & 1;
+      const int mt = col >> 4, odd = (col >> 3) & 1, gg = col & 7;
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + odd * 2 + (rem & 1);
       const float hi = tf32_hi(v);
       Whi[dst] = hi;
@@ -184,6 +215,9 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   const int64_t n_tiles = ((int64_t)n + R - 1) / R;
   const int64_t wt0 = split ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * warps + warp;
   const int64_t wt_stride = split ? (int64_t)gridDim.x : (int64_t)gridDim.x * warps;
+  const char* const in_l = reinterpret_cast<const char*>(p.in) + 16 * t;
+  const uint32_t ldb = (uint32_t)p.ldi * 4u;  // row stride in bytes
+  const int4* const rec_l = p.g_rec + g;
   for (int64_t wt = wt0; wt < n_tiles; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
@@ -198,124 +232,122 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
     }
     __syncwarp();
 
-    // two-level prefetch: group records travel 2*DEPTH groups ahead of the MMAs, the feature rows they
-    // point to DEPTH groups ahead.  Records and rows past the end of the range are clamped to the last
-    // group: redundant but unconditional loads, never consumed.
+    // Software pipeline over a ring of RING record slots and DEPTH row slots; the loop body is unrolled
+    // RING times so that every slot index is static and no value is ever copied between slots (a copy
+    // of a just-issued load stalls the warp until the load returns).  Records and rows past the end of
+    // the range are clamped to the last group: redundant but unconditional loads, never consumed.
+    int Rx[RING], Ry[RING], Rz[RING];
     float4 G[DEPTH][2][Q];
-    int4 M[DEPTH], Mn[DEPTH];
     const int g_last = max(ge - 1, gb);
-    const int4* rec_l = p.g_rec + g;
-    const float4* in_l = reinterpret_cast<const float4*>(p.in) + t;
-    const int ld4 = p.ldi >> 2;  // row stride in float4 (ldi % 4 == 0)
-    auto fetch_rec = [&](int grp, int d) { Mn[d] = __ldg(rec_l + (int64_t)min(grp, g_last) * 8); };
-    auto fetch = [&](int grp, int d) {
-      M[d] = Mn[d];
-      const float4* s0 = in_l + (int64_t)M[d].x * ld4;
-      const float4* s1 = in_l + (int64_t)M[d].y * ld4;
+    auto fetch_rec = [&](int grp, int u) {
+      const int4* r = rec_l + (int64_t)min(grp, g_last) * 8;
+      Rx[u] = ldg_nc32(r);
+      Ry[u] = ldg_nc32(reinterpret_cast<const int*>(r) + 1);
+      Rz[u] = ldg_nc32(reinterpret_cast<const int*>(r) + 2);
+    };
+    auto fetch_rows = [&](int u, int d) {
+      const float4* s0 = reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)Rx[u] * ldb);
+      const float4* s1 = reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)Ry[u] * ldb);
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         G[d][0][q] = __ldg(s0 + 4 * q);
         G[d][1][q] = __ldg(s1 + 4 * q);
       }
-      fetch_rec(grp + DEPTH, d);
     };
     if (gb < ge) {
 #pragma unroll
-      for (int d = 0; d < DEPTH; ++d) fetch_rec(gb + d, d);
+      for (int u = 0; u < RING; ++u) fetch_rec(gb + u, u);
 #pragma unroll
-      for (int d = 0; d < DEPTH; ++d) fetch(gb + d, d);
+      for (int d = 0; d < DEPTH; ++d) fetch_rows(d, d);
     }
 
-    for (int g0 = gb; g0 < ge; g0 += DEPTH) {
+    for (int g0 = gb; g0 < ge; g0 += RING) {
 #pragma unroll
-      for (int d = 0; d < DEPTH; ++d) {
-        const int grp = g0 + d;
-        if (grp < ge) {
-          const uint32_t mz = (uint32_t)M[d].z;
-          const int kk = (mz >> 16) & 0xff;
-          const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
-          float4* const r0 = acc + o0 * C4;
-          float4* const r1 = acc + o1 * C4;
-          const int x0 = SWZ ? ((o0 & 1) << 2) : 0, x1 = SWZ ? ((o1 & 1) << 2) : 0;
-          // C operand: the rows' running sums (n-tile 2mt holds channels 4t, 4t+1 of 16-channel block mt,
-          // n-tile 2mt+1 holds 4t+2, 4t+3)
-          float dacc[MT][2][4];
+      for (int u = 0; u < RING; ++u) {
+        const int grp = g0 + u;
+        if (grp >= ge) break;
+        const int d = u % DEPTH;
+        const uint32_t mz = (uint32_t)Rz[u];
+        const int kk = (mz >> 16) & 0xff;
+        const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
+        const int x0 = (MT & 1) ? ((o0 >> 1) & 1) : (o0 & 3), x1 = (MT & 1) ? ((o1 >> 1) & 1) : (o1 & 3);
+        const uint32_t a0 = s_acc + o0 * (CT * 4), a1 = s_acc + o1 * (CT * 4);
+        // C operand: the running sums of the 16 output rows
+        float dacc[NT][4];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const float4 v0 = r0[(4 * mt + t) ^ x0], v1 = r1[(4 * mt + t) ^ x1];
-            dacc[mt][0][0] = v0.x; dacc[mt][0][1] = v0.y; dacc[mt][0][2] = v1.x; dacc[mt][0][3] = v1.y;
-            dacc[mt][1][0] = v0.z; dacc[mt][1][1] = v0.w; dacc[mt][1][2] = v1.z; dacc[mt][1][3] = v1.w;
-          }
-          const int kwt = p.kflip ? (K - 1 - kk) : kk;
-          const float* wk = WSMEM ? nullptr : p.W + (int64_t)kwt * p.w_sk + (int64_t)(4 * t) * p.w_si +
-                                                  (int64_t)(cob + 4 * (g >> 1) + (g & 1)) * p.w_so;
-          const int wk_off = kk * (KS * MT * 128) + lane * 4;
+        for (int j = 0; j < NT; ++j) {
+          const float2 c01 = lds64(a0 + ((j ^ x0) << 5)), c23 = lds64(a1 + ((j ^ x1) << 5));
+          dacc[j][0] = c01.x; dacc[j][1] = c01.y; dacc[j][2] = c23.x; dacc[j][3] = c23.y;
+        }
+        const int kwt = p.kflip ? (K - 1 - kk) : kk;
+        const float* wk = WSMEM ? nullptr : p.W + (int64_t)kwt * p.w_sk + (int64_t)(4 * t) * p.w_si +
+                                                (int64_t)(cob + g) * p.w_so;
+        const uint32_t wk_off = (uint32_t)kk * (KS * MT * 512);
 #pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            const float f0[4] = {G[d][0][q].x, G[d][0][q].y, G[d][0][q].z, G[d][0][q].w};
-            const float f1[4] = {G[d][1][q].x, G[d][1][q].y, G[d][1][q].z, G[d][1][q].w};
+        for (int q = 0; q < Q; ++q) {
+          const float f0[4] = {G[d][0][q].x, G[d][0][q].y, G[d][0][q].z, G[d][0][q].w};
+          const float f1[4] = {G[d][1][q].x, G[d][1][q].y, G[d][1][q].z, G[d][1][q].w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int s = 2 * q + h;
-              // a0 = (pair g, ci 4t+2h), a1 = (pair g+8, same ci), a2 = (pair g, ci+1), a3 = (pair g+8, ci+1)
-              const float av[4] = {f0[2 * h], f1[2 * h], f0[2 * h + 1], f1[2 * h + 1]};
-              uint32_t ah[4], al[4];
+          for (int h = 0; h < 2; ++h) {
+            const int s = 2 * q + h;
+            const float av[4] = {f0[2 * h], f1[2 * h], f0[2 * h + 1], f1[2 * h + 1]};
+            uint32_t ah[4], al[4];
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                // single-pass tf32: raw fp32 bits (the tensor core ignores the low mantissa bits)
-                const float hi = X3 ? tf32_hi(av[r]) : av[r];
-                ah[r] = __float_as_uint(hi);
-                al[r] = __float_as_uint(av[r] - hi);
+            for (int r = 0; r < 4; ++r) {
+              // Every fragment register is DEFINED by an instruction ptxas cannot see through: it knows the
+              // tensor core ignores the low mantissa bits, drops a plain mask in front of an HMMA and then
+              // re-assembles the operand quad with four MOVs in front of every single HMMA that uses it.
+              if (X3) {
+                const float lo = av[r] - tf32_hi(av[r]);
+                al[r] = __float_as_uint(lo);
+                ah[r] = __float_as_uint(av[r] - lo);  // == tf32_hi(av[r]), exactly
+              } else {
+                ah[r] = __float_as_uint(av[r]) & p.ones;  // single pass: raw fp32 bits
+              }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              uint32_t bh[2][2], bl[2][2];
+              if (WSMEM) {
+                const float4 b4 = lds128(s_whi + wk_off + (s * MT + mt) * 512);
+                bh[0][0] = __float_as_uint(b4.x); bh[0][1] = __float_as_uint(b4.y);
+                bh[1][0] = __float_as_uint(b4.z); bh[1][1] = __float_as_uint(b4.w);
+                if (X3) {
+                  const float4 l4 = lds128(s_wlo + wk_off + (s * MT + mt) * 512);
+                  bl[0][0] = __float_as_uint(l4.x); bl[0][1] = __float_as_uint(l4.y);
+                  bl[1][0] = __float_as_uint(l4.z); bl[1][1] = __float_as_uint(l4.w);
+                }
+              } else {
+                const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
+                const float w4[4] = {__ldg(wp), __ldg(wp + p.w_si), __ldg(wp + 8 * p.w_so),
+                                     __ldg(wp + p.w_si + 8 * p.w_so)};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float hi = X3 ? tf32_hi(w4[r]) : w4[r];
+                  bh[r >> 1][r & 1] = __float_as_uint(hi);
+                  bl[r >> 1][r & 1] = __float_as_uint(w4[r] - hi);
+                }
               }
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                float w4[4];
-                if (WSMEM) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(Whi + wk_off + (s * MT + mt) * 128);
-                  w4[0] = b4.x; w4[1] = b4.y; w4[2] = b4.z; w4[3] = b4.w;
-                } else {
-                  const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
-                  w4[0] = __ldg(wp);
-                  w4[1] = __ldg(wp + p.w_si);
-                  w4[2] = __ldg(wp + 2 * p.w_so);
-                  w4[3] = __ldg(wp + p.w_si + 2 * p.w_so);
+              for (int o = 0; o < 2; ++o) {
+                if (X3) {
+                  mma_tf32(dacc[2 * mt + o], al, bh[o]);
+                  mma_tf32(dacc[2 * mt + o], ah, bl[o]);
                 }
-                uint32_t bh[2][2], bl[2][2];
-                if (WSMEM) {
-#pragma unroll
-                  for (int r = 0; r < 4; ++r) bh[r >> 1][r & 1] = __float_as_uint(w4[r]);
-                  if (X3) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(Wlo + wk_off + (s * MT + mt) * 128);
-                    bl[0][0] = __float_as_uint(l4.x); bl[0][1] = __float_as_uint(l4.y);
-                    bl[1][0] = __float_as_uint(l4.z); bl[1][1] = __float_as_uint(l4.w);
-                  }
-                } else {
-#pragma unroll
-                  for (int r = 0; r < 4; ++r) {
-                    const float hi = X3 ? tf32_hi(w4[r]) : w4[r];
-                    bh[r >> 1][r & 1] = __float_as_uint(hi);
-                    bl[r >> 1][r & 1] = __float_as_uint(w4[r] - hi);
-                  }
-                }
-#pragma unroll
-                for (int o = 0; o < 2; ++o) {
-                  if (X3) {
-                    mma_tf32(dacc[mt][o], al, bh[o]);
-                    mma_tf32(dacc[mt][o], ah, bl[o]);
-                  }
-                  mma_tf32(dacc[mt][o], ah, bh[o]);
-                }
+                mma_tf32(dacc[2 * mt + o], ah, bh[o]);
               }
             }
           }
-          fetch(grp + DEPTH, d);  // this slot is free again
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            r0[(4 * mt + t) ^ x0] = make_float4(dacc[mt][0][0], dacc[mt][0][1], dacc[mt][1][0], dacc[mt][1][1]);
-            r1[(4 * mt + t) ^ x1] = make_float4(dacc[mt][0][2], dacc[mt][0][3], dacc[mt][1][2], dacc[mt][1][3]);
-          }
-          __syncwarp();
         }
+        // refill the two slots this group has just released
+        fetch_rows((u + DEPTH) % RING, d);
+        fetch_rec(grp + RING, u);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          sts64(a0 + ((j ^ x0) << 5), dacc[j][0], dacc[j][1]);
+          sts64(a1 + ((j ^ x1) << 5), dacc[j][2], dacc[j][3]);
+        }
+        __syncwarp();
       }
     }
 
@@ -327,7 +359,8 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
     for (int e = e_begin; e < R * C4; e += e_step) {
       const int row = e / C4, c4 = e - row * C4;
       if (base + row < n) {
-        const int src = row * C4 + (c4 ^ (SWZ ? ((row & 1) << 2) : 0));
+        const int xr = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
+        const int src = row * C4 + ((((c4 >> 1) ^ xr) << 1) | (c4 & 1));
         float4 v;
         if (split) {
           v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -530,7 +563,7 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, in
     p.in = in + c0; p.ldi = (int)ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = (int)w_sk; p.w_si = (int)w_si;
     p.w_so = (int)w_so; p.kflip = kflip; p.tile_off = tile_off; p.g_rec = reinterpret_cast<const int4*>(g_rec);
     p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out;
-    p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.warps = pl.warps; p.split = pl.split;
+    p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.warps = pl.warps; p.split = pl.split; p.ones = 0xffffffffu;
     int rc;
     switch (pl.Q) {
       case 1: rc = launch_gpl_q<1>(p, pl, tile_rows, x3, st); break;
