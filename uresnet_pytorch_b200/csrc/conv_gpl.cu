@@ -168,11 +168,16 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
   constexpr int DEPTH = Q == 1 ? 2 : 1;  // feature rows are fetched DEPTH groups ahead, records 2*DEPTH
   constexpr int RING = 2 * DEPTH;
+  // WREG: the B fragments of the current offset live in registers and are reloaded (raw fp32 from shared
+  // memory, low parts recomputed) only when the offset changes -- the L1/shared data pipe is this
+  // kernel's bottleneck (profiles/README.md), and the weights were a third of its shared-memory traffic
+  constexpr bool WREG = WSMEM && (Q * MT <= 2);
+  constexpr bool WLO = WSMEM && X3 && !WREG;  // separate low-part copy in shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
   const int split = p.split;
-  if (split ? ((int64_t)blockIdx.x * R >= n) : ((int64_t)blockIdx.x * warps * R >= n)) return;
+  if (split ? ((int64_t)blockIdx.x * R >= n) : (n == 0)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   float* Whi = reinterpret_cast<float*>(smem_raw);
   float* Wlo = Whi + w_elems;
   constexpr int kAccBytes = (R + 1) * CT * 4;
-  const int acc_base = w_elems * 4 * (X3 ? 2 : 1);
+  const int acc_base = w_elems * 4 * (WLO ? 2 : 1);
   float4* const acc = reinterpret_cast<float4*>(smem_raw + acc_base + warp * kAccBytes);
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t s_acc = s_base + acc_base + warp * kAccBytes + t * 8;  // + row * CT * 4 + chunk * 32
@@ -206,19 +211,40 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       const int mt = col >> 4, odd = (col >> 3) & 1, gg = col & 7;
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + odd * 2 + (rem & 1);
       const float hi = tf32_hi(v);
-      Whi[dst] = hi;
-      if (X3) Wlo[dst] = v - hi;
+      Whi[dst] = WREG ? v : hi;
+      if (WLO) Wlo[dst] = v - hi;
     }
     __syncthreads();
   }
 
   const int64_t n_tiles = ((int64_t)n + R - 1) / R;
-  const int64_t wt0 = split ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * warps + warp;
-  const int64_t wt_stride = split ? (int64_t)gridDim.x : (int64_t)gridDim.x * warps;
+  // Tile -> warp assignment.  Split mode: tile = CTA.  Otherwise every warp takes a CONTIGUOUS range of
+  // tiles of (nearly) equal cost, cost(tile) = groups + kTileCost: the work per tile varies 10x between
+  // track and shower regions, and a round-robin assignment left the SMs idle for 20% of the kernel.
+  // cost is monotone in the tile index (prefix sums), so the range bounds are two binary searches.
+  constexpr int kTileCost = 4;
+  int64_t wt_begin, wt_end, wt_stride;
+  if (split) {
+    wt_begin = blockIdx.x; wt_end = n_tiles; wt_stride = gridDim.x;
+  } else {
+    const int64_t nw = (int64_t)gridDim.x * warps, w = (int64_t)blockIdx.x * warps + warp;
+    const int64_t total = (int64_t)__ldg(p.tile_off + n_tiles) + kTileCost * n_tiles;
+    const int64_t lo_cost = total * w / nw, hi_cost = total * (w + 1) / nw;
+    // first tile t with prefix cost(t) = tile_off[t] + kTileCost * t >= bound
+    int64_t a0 = 0, a1 = n_tiles, b0 = 0, b1 = n_tiles;
+    while (a0 < a1 || b0 < b1) {
+      const int64_t ma = (a0 + a1) >> 1, mb = (b0 + b1) >> 1;
+      const int64_t ca = (int64_t)__ldg(p.tile_off + ma) + kTileCost * ma;
+      const int64_t cb = (int64_t)__ldg(p.tile_off + mb) + kTileCost * mb;
+      if (a0 < a1) { if (ca >= lo_cost) a1 = ma; else a0 = ma + 1; }
+      if (b0 < b1) { if (cb >= hi_cost) b1 = mb; else b0 = mb + 1; }
+    }
+    wt_begin = a0; wt_end = (w == nw - 1) ? n_tiles : b0; wt_stride = 1;
+  }
   const char* const in_l = reinterpret_cast<const char*>(p.in) + 16 * t;
   const uint32_t ldb = (uint32_t)p.ldi * 4u;  // row stride in bytes
   const int4* const rec_l = p.g_rec + g;
-  for (int64_t wt = wt0; wt < n_tiles; wt += wt_stride) {
+  for (int64_t wt = wt_begin; wt < wt_end; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
     for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,6 +287,8 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       for (int d = 0; d < DEPTH; ++d) fetch_rows(d, d);
     }
 
+    uint32_t wbh[WREG ? KS : 1][WREG ? MT : 1][4], wbl[WREG ? KS : 1][WREG ? MT : 1][4];
+    int wcur = -1;
     for (int g0 = gb; g0 < ge; g0 += RING) {
 #pragma unroll
       for (int u = 0; u < RING; ++u) {
@@ -283,6 +311,21 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
         const float* wk = WSMEM ? nullptr : p.W + (int64_t)kwt * p.w_sk + (int64_t)(4 * t) * p.w_si +
                                                 (int64_t)(cob + g) * p.w_so;
         const uint32_t wk_off = (uint32_t)kk * (KS * MT * 512);
+        if (WREG && kk != wcur) {
+          wcur = kk;
+#pragma unroll
+          for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const float4 b4 = lds128(s_whi + wk_off + (s * MT + mt) * 512);
+              const float w4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                wbh[WREG ? s : 0][WREG ? mt : 0][r] = __float_as_uint(w4[r]);  // the tensor core truncates
+                wbl[WREG ? s : 0][WREG ? mt : 0][r] = __float_as_uint(w4[r] - tf32_hi(w4[r]));
+              }
+            }
+        }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float f0[4] = {G[d][0][q].x, G[d][0][q].y, G[d][0][q].z, G[d][0][q].w};
@@ -308,7 +351,13 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               uint32_t bh[2][2], bl[2][2];
-              if (WSMEM) {
+              if (WREG) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  bh[r >> 1][r & 1] = wbh[WREG ? s : 0][WREG ? mt : 0][r];
+                  bl[r >> 1][r & 1] = wbl[WREG ? s : 0][WREG ? mt : 0][r];
+                }
+              } else if (WSMEM) {
                 const float4 b4 = lds128(s_whi + wk_off + (s * MT + mt) * 512);
                 bh[0][0] = __float_as_uint(b4.x); bh[0][1] = __float_as_uint(b4.y);
                 bh[1][0] = __float_as_uint(b4.z); bh[1][1] = __float_as_uint(b4.w);
@@ -395,6 +444,12 @@ struct GPlan {
 };
 
 size_t acc_bytes(int R, int mt) { return (size_t)(R + 1) * (16 * mt) * 4; }
+// shared-memory weight copy of the WSMEM variants: raw fp32 when the fragments are register-cached
+// (Q * MT <= 2, see WREG), else separate high and low parts for tf32x3
+size_t w_smem_bytes(int K, int Cin, int mt, int x3) {
+  const bool wreg = (Cin / 16) * mt <= 2;
+  return (size_t)K * Cin * 16 * mt * 4 * ((x3 && !wreg) ? 2 : 1);
+}
 
 GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3, int R) {
   GPlan pl{};
@@ -408,7 +463,7 @@ GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3, int R) {
   if (large) {
     for (int mt = 2; mt >= 1; --mt) {
       if (cot % mt != 0) continue;
-      if ((size_t)K * Cin * 16 * mt * 4 * (x3 ? 2 : 1) + 12 * acc_bytes(R, mt) <= (size_t)kMaxSmem) {
+      if (w_smem_bytes(K, Cin, mt, x3) + 12 * acc_bytes(R, mt) <= (size_t)kMaxSmem) {
         pl.MT = mt;
         break;
       }
@@ -419,7 +474,7 @@ GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3, int R) {
     pl.MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
   }
   pl.passes = cot / pl.MT;
-  const size_t wbytes = (size_t)K * Cin * 16 * pl.MT * 4 * (x3 ? 2 : 1);
+  const size_t wbytes = w_smem_bytes(K, Cin, pl.MT, x3);
   pl.wsmem = large && (wbytes + 12 * acc_bytes(R, pl.MT) <= (size_t)kMaxSmem);
   pl.split = large ? 0 : 1;
   const size_t fixed = pl.wsmem ? wbytes : 0;
