@@ -99,19 +99,23 @@ int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_de
                        void* stream);
 
 /* Grouped pair lists (GPL): the rulebook of one (level, layer type) in the form the tensor-core
- * convolution consumes -- per tile of `tile_rows` (64 or 128) output rows, the rule pairs of every offset
- * packed into groups of 16 (csrc/conv_gpl.cu).  Built once per level, shared by every forward / dgrad use.
- * Source of the pairs: `table` (offset-major, as above), or parent/kofs (Deconvolution-style:
+ * convolution consumes -- per tile of `tile_rows` (32, 64 or 128) output rows, the rule pairs of every
+ * offset packed into groups of 16 (csrc/conv_gpl.cu).  Built once per level, shared by every forward /
+ * dgrad use.  Source of the pairs: `table` (offset-major, as above), or parent/kofs (Deconvolution-style:
  * pair (parent[p] -> p) at offset kofs[p]), or neither (identity, K == 1).
  * Record format: g_rec[group][8] int4; entry j = { in row of pair j, in row of pair j+8,
  * out(j) | out(j+8) << 8 | k << 16, 0 } with out = row inside the tile (tile_rows = padding slot).
- * stage 0 -> tile_off[tiles + 1], total_dev[1];  stage 1 -> g_rec[128 B * cap_groups]. */
-int b200scn_gpl_tile_rows(int64_t n_cap); /* recommended tile_rows for a level of n_cap rows */
+ * stage 0 -> tile_off[tiles + 1] (scanned group offsets), total_dev[1];
+ * stage 1 -> g_rec[128 B * cap_groups] at those offsets (tile t = groups tile_off[t] .. tile_off[t+1]);
+ * stage 2 -> single pass, fixed-stride slots: tile_off[tiles] = begin, tile_end[tiles] = end of every tile,
+ *            cap_groups >= b200scn_gpl_max_groups(); no scan and no read-back (CUDA-graph regime). */
+int b200scn_gpl_tile_rows(int64_t n); /* recommended tile_rows for a level of n rows */
 int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows);
 int64_t b200scn_gpl_scratch_bytes(int64_t n_cap);
 int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs, int K,
-                      int64_t n_cap, const int32_t* n_dev, int tile_rows, int32_t* tile_off, int32_t* total_dev,
-                      void* g_rec, int64_t cap_groups, void* scratch, int64_t scratch_bytes, void* stream);
+                      int64_t n_cap, const int32_t* n_dev, int tile_rows, int32_t* tile_off, int32_t* tile_end,
+                      int32_t* total_dev, void* g_rec, int64_t cap_groups, void* scratch, int64_t scratch_bytes,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (ii) gather-GEMM(-scatter) convolutions -- SubmanifoldConvolution / Convolution /
@@ -126,11 +130,20 @@ int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_s
                        const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
                        int math_mode, void* stream);
 
-/* the same contraction driven by a grouped pair list (tensor-core math modes, channels % 16 == 0) */
-int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so, int kflip,
-                     int tile_rows, const int32_t* tile_off, const void* g_rec, int K, int64_t n_out_cap,
-                     const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
-                     int math_mode, void* stream);
+/* the same contraction driven by a grouped pair list (tensor-core math modes, channels % 16 == 0);
+ * tile_end == NULL: scanned lists (stage 0 + 1), else fixed-stride lists (stage 2) */
+/* Wp: optional fragment-ordered copy of W for this direction (b200scn_pack_weights with the same strides
+ * and kflip), or NULL */
+int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
+                     int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end, const void* g_rec, int K,
+                     int64_t n_out_cap, const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo,
+                     int accumulate, int math_mode, void* stream);
+
+/* Re-order weights into the mma fragment order b200scn_conv_gpl reads with coalesced 16-byte loads.
+ * jobs_dev: device array of n_jobs records of int64[10] = {W ptr, out ptr, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0}
+ * (Cin/Cout/strides of the DIRECTION the copy serves: forward = (nIn, nOut, nOut, 1), dgrad = (nOut, nIn, 1, nOut));
+ * out holds K*Cin*Cout floats; max_elems = largest K*Cin*Cout among the jobs.  One launch for all jobs. */
+int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, void* stream);
 
 /* out[p, :] = in[parent[p], :] @ W[kofs[p]]
  * serves: Deconvolution fwd; Convolution dgrad (transposed weight strides). */

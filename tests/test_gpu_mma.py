@@ -109,7 +109,7 @@ def test_mma_large_batch_against_fp32_kernel():
     assert (a - c).abs().max().item() <= 5e-3 * a.abs().max().item()
 
 
-@pytest.mark.parametrize("tile_rows", [64, 128])
+@pytest.mark.parametrize("tile_rows", [32, 64, 128])
 def test_grouped_pair_lists_match_table(tile_rows, monkeypatch):
     """The GPL builder reproduces exactly the (offset, in, out) triples of the neighbour table."""
     import numpy as np

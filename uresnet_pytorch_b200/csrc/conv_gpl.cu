@@ -55,7 +55,7 @@ template <bool FILL, int R>
 __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const int32_t* __restrict__ parent,
                             const uint8_t* __restrict__ kofs, int K, int64_t n_cap, const int32_t* __restrict__ n_dev,
                             int32_t* __restrict__ tile_cnt, const int32_t* __restrict__ tile_off,
-                            int4* __restrict__ g_rec, int64_t cap_groups) {
+                            int32_t* __restrict__ tile_beg_out, int4* __restrict__ g_rec, int64_t cap_groups) {
   constexpr int NR = R / 32;  // rows per lane
   const int n = live_rows(n_dev, n_cap);
   const int lane = threadIdx.x & 31;
@@ -72,7 +72,11 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
       const int r = base + 32 * i + lane;
       if (parent != nullptr && r < n) { pk[i] = kofs[r]; pp[i] = __ldg(parent + r); }
     }
-    int64_t grp = FILL ? (int64_t)tile_off[tile] : 0;
+    // fixed-stride mode (FILL && tile_cnt): tile t owns the slots [t * stride, (t + 1) * stride) and the
+    // builder publishes its begin/end itself -- one pass, no count + scan
+    const bool fixed = FILL && tile_beg_out != nullptr;
+    int64_t grp = FILL ? (fixed ? tile * (int64_t)K * (R / 16) : (int64_t)tile_off[tile]) : 0;
+    const int64_t grp0 = grp;
     int count = 0;
     for (int k = 0; k < K; ++k) {
       int e[NR], pre[NR];
@@ -117,6 +121,10 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
       count += ng;
     }
     if (!FILL && lane == 0) tile_cnt[tile] = count;
+    if (fixed && lane == 0) {
+      tile_beg_out[tile] = (int32_t)grp0;
+      tile_cnt[tile] = (int32_t)(grp0 + count);  // = tile_end
+    }
   }
 }
 
@@ -124,7 +132,9 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
 struct GplParams {
   const float* in; int ldi;
   const float* W; int w_sk, w_si, w_so; int kflip;
-  const int32_t* tile_off; const int4* g_rec;
+  const float* Wp; int cot;  // fragment-ordered copy of W for this direction (b200scn_pack_weights), Cout / 16
+  const int32_t* tile_off; const int32_t* tile_end; const int4* g_rec;  // tile_end == NULL: tile_off + 1
+  int Q;  // Cin / 16 (runtime value for k_conv_gpl_small)
   int K;
   int64_t n_cap; const int32_t* n_dev;
   float* out; int ldo; int accumulate;
@@ -437,98 +447,303 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   }
 }
 
-struct GPlan {
-  int Q, MT, passes, warps, split, ctas_per_sm;
-  bool wsmem, ok;
-  size_t smem;
+// ---- small inputs ----------------------------------------------------------------------------------
+// One CTA per (tile, pass of CT = 16 MT output channels); its 8 warps split the tile's groups, each with
+// a private partial accumulator, and the partials are summed in warp order.  Any Cin % 16 == 0 in ONE
+// launch: the input channels are walked in 16-channel chunks (runtime loop), chunk q+1 -- feature rows
+// and weight fragments, both straight from L1/L2 -- in flight while chunk q is on the tensor pipe.
+// Same fragment <-> channel maps as k_conv_gpl.
+template <int MT>
+struct GplChunk {
+  float4 f0, f1;      // channels 16q + 4t .. +3 of the rows of pairs g and g+8
+  float w[2][MT][4];  // [h][mt] = {b0, b1 of n-tile 2mt, b0, b1 of n-tile 2mt+1}
 };
 
+template <int MT, bool X3, int R, bool PACKED>
+__global__ void __launch_bounds__(512) k_conv_gpl_small(const GplParams p) {
+  constexpr int CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = live_rows(p.n_dev, p.n_cap);
+  if ((int64_t)blockIdx.x * R >= n) return;
+  const int warps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = p.K, Q = p.Q;
+  const int cob = blockIdx.y * CT;
+  constexpr int kAccBytes = (R + 1) * CT * 4;
+  float4* const acc = reinterpret_cast<float4*>(smem_raw + warp * kAccBytes);
+  const uint32_t s_acc = (uint32_t)__cvta_generic_to_shared(smem_raw) + warp * kAccBytes + t * 8;
+  const char* const in_l = reinterpret_cast<const char*>(p.in) + 16 * t;
+  const uint32_t ldb = (uint32_t)p.ldi * 4u;
+  const int4* const rec_l = p.g_rec + g;
+  const int64_t n_tiles = ((int64_t)n + R - 1) / R;
+  const float* const w_l = p.W + (int64_t)(4 * t) * p.w_si + (int64_t)(cob + g) * p.w_so;
+
+  for (int64_t wt = blockIdx.x; wt < n_tiles; wt += gridDim.x) {
+    const int base = (int)(wt * R);
+    __syncwarp();
+    for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int gb = __ldg(p.tile_off + wt), ge = __ldg((p.tile_end ? p.tile_end : p.tile_off + 1) + wt);
+    {
+      const int per = (ge - gb + warps - 1) / warps;
+      const int b2 = gb + warp * per;
+      ge = min(ge, b2 + per);
+      gb = min(b2, ge);
+    }
+    __syncwarp();
+    if (gb < ge) {
+      const int g_last = ge - 1;
+      auto load_rec = [&](int grp, int& x, int& y, int& z) {
+        const int* r = reinterpret_cast<const int*>(rec_l + (int64_t)min(grp, g_last) * 8);
+        x = ldg_nc32(r); y = ldg_nc32(r + 1); z = ldg_nc32(r + 2);
+      };
+      // PACKED: one coalesced LDG.128 per (h, mt) from the fragment-ordered copy (the offset flip is
+      // already folded into it); else four scalar loads from the strided original -- 4x the L1 wavefronts
+      const float* const wp_l = p.Wp + (size_t)(cob >> 4) * 128 + lane * 4;
+      auto w_of = [&](int z) {
+        const int kk = (z >> 16) & 0xff;
+        if (PACKED) return wp_l + (size_t)kk * Q * 2 * p.cot * 128;
+        return w_l + (int64_t)(p.kflip ? (K - 1 - kk) : kk) * p.w_sk;
+      };
+      auto load_chunk = [&](GplChunk<MT>& c, int x, int y, const float* wk, int q) {
+        c.f0 = __ldg(reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)x * ldb) + 4 * q);
+        c.f1 = __ldg(reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)y * ldb) + 4 * q);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (PACKED) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(wk + (size_t)((2 * q + h) * p.cot + mt) * 128));
+              c.w[h][mt][0] = v.x; c.w[h][mt][1] = v.y; c.w[h][mt][2] = v.z; c.w[h][mt][3] = v.w;
+            } else {
+              const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
+              c.w[h][mt][0] = __ldg(wp);
+              c.w[h][mt][1] = __ldg(wp + p.w_si);
+              c.w[h][mt][2] = __ldg(wp + 8 * p.w_so);
+              c.w[h][mt][3] = __ldg(wp + p.w_si + 8 * p.w_so);
+            }
+          }
+      };
+      // records run two groups ahead of the group on the tensor pipe, chunks one chunk ahead
+      int x0, y0, z0, x1, y1, z1, x2, y2, z2;
+      load_rec(gb, x0, y0, z0);
+      load_rec(gb + 1, x1, y1, z1);
+      GplChunk<MT> cur, nxt;
+      load_chunk(cur, x0, y0, w_of(z0), 0);
+      for (int grp = gb; grp < ge; ++grp) {
+        load_rec(grp + 2, x2, y2, z2);
+        const int o0 = z0 & 0xff, o1 = (z0 >> 8) & 0xff;
+        const int xs0 = (MT & 1) ? ((o0 >> 1) & 1) : (o0 & 3), xs1 = (MT & 1) ? ((o1 >> 1) & 1) : (o1 & 3);
+        const uint32_t a0 = s_acc + o0 * (CT * 4), a1 = s_acc + o1 * (CT * 4);
+        float dacc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float2 c01 = lds64(a0 + ((j ^ xs0) << 5)), c23 = lds64(a1 + ((j ^ xs1) << 5));
+          dacc[j][0] = c01.x; dacc[j][1] = c01.y; dacc[j][2] = c23.x; dacc[j][3] = c23.y;
+        }
+        const float* const wk0 = w_of(z0);
+        const float* const wk1 = w_of(z1);
+        for (int q = 0; q < Q; ++q) {
+          if (q + 1 < Q) load_chunk(nxt, x0, y0, wk0, q + 1);
+          else load_chunk(nxt, x1, y1, wk1, 0);  // first chunk of the next group (clamped at the end: unused)
+          const float f0[4] = {cur.f0.x, cur.f0.y, cur.f0.z, cur.f0.w};
+          const float f1[4] = {cur.f1.x, cur.f1.y, cur.f1.z, cur.f1.w};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float av[4] = {f0[2 * h], f1[2 * h], f0[2 * h + 1], f1[2 * h + 1]};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (X3) {
+                const float lo = av[r] - tf32_hi(av[r]);
+                al[r] = __float_as_uint(lo);
+                ah[r] = __float_as_uint(av[r] - lo);
+              } else {
+                ah[r] = __float_as_uint(av[r]) & p.ones;
+              }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float wv = cur.w[h][mt][r];
+                bh[r >> 1][r & 1] = __float_as_uint(wv);  // the tensor core truncates to tf32 itself
+                bl[r >> 1][r & 1] = __float_as_uint(wv - tf32_hi(wv));
+              }
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                if (X3) {
+                  mma_tf32(dacc[2 * mt + o], al, bh[o]);
+                  mma_tf32(dacc[2 * mt + o], ah, bl[o]);
+                }
+                mma_tf32(dacc[2 * mt + o], ah, bh[o]);
+              }
+            }
+          }
+          cur = nxt;
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          sts64(a0 + ((j ^ xs0) << 5), dacc[j][0], dacc[j][1]);
+          sts64(a1 + ((j ^ xs1) << 5), dacc[j][2], dacc[j][3]);
+        }
+        __syncwarp();
+        x0 = x1; y0 = y1; z0 = z1;
+        x1 = x2; y1 = y2; z1 = z2;
+      }
+    }
+    __syncthreads();
+    const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const float4* acc0 = reinterpret_cast<const float4*>(smem_raw);
+    for (int e = tid; e < R * C4; e += blockDim.x) {
+      const int row = e / C4, c4 = e - row * C4;
+      if (base + row < n) {
+        const int xr = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
+        const int src = row * C4 + ((((c4 >> 1) ^ xr) << 1) | (c4 & 1));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < warps; ++w) {
+          const float4 u = acc0[w * (kAccBytes / 16) + src];
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
+        if (vec_ok) {
+          if (p.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(o);
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o) = v;
+        } else {
+          if (p.accumulate) { v.x += o[0]; v.y += o[1]; v.z += o[2]; v.w += o[3]; }
+          o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 size_t acc_bytes(int R, int mt) { return (size_t)(R + 1) * (16 * mt) * 4; }
-// shared-memory weight copy of the WSMEM variants: raw fp32 when the fragments are register-cached
+// shared-memory weight copy of k_conv_gpl: raw fp32 when the fragments are register-cached
 // (Q * MT <= 2, see WREG), else separate high and low parts for tf32x3
 size_t w_smem_bytes(int K, int Cin, int mt, int x3) {
   const bool wreg = (Cin / 16) * mt <= 2;
   return (size_t)K * Cin * 16 * mt * 4 * ((x3 && !wreg) ? 2 : 1);
 }
 
-GPlan plan_gpl(int K, int Cin, int Cout, int64_t n_cap, int x3, int R) {
-  GPlan pl{};
-  pl.ok = false;
-  if (Cin % 16 || Cout % 16 || Cin > 64 || Cin < 16) return pl;
-  pl.Q = Cin / 16;
-  const int cot = Cout / 16;
-  // large: enough tiles to give every SM a CTA full of one-tile warps
-  const bool large = R == 128 && n_cap >= (int64_t)R * 8 * sm_count();
-  pl.MT = 1;
-  if (large) {
-    for (int mt = 2; mt >= 1; --mt) {
-      if (cot % mt != 0) continue;
-      if (w_smem_bytes(K, Cin, mt, x3) + 12 * acc_bytes(R, mt) <= (size_t)kMaxSmem) {
-        pl.MT = mt;
-        break;
-      }
-    }
-  } else {
-    // small inputs: narrow passes until the grid covers the SMs
-    const int64_t tiles = cdiv(n_cap, R);
-    pl.MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
-  }
-  pl.passes = cot / pl.MT;
-  const size_t wbytes = w_smem_bytes(K, Cin, pl.MT, x3);
-  pl.wsmem = large && (wbytes + 12 * acc_bytes(R, pl.MT) <= (size_t)kMaxSmem);
-  pl.split = large ? 0 : 1;
-  const size_t fixed = pl.wsmem ? wbytes : 0;
-  static int large_warps = 0;  // B200SCN_GPL_WARPS: warps per CTA of the large-input variant (A/B runs)
-  if (large_warps == 0) {
+int large_warps() {
+  static int v = 0;  // B200SCN_GPL_WARPS: warps per CTA of the large-input kernel (A/B runs)
+  if (v == 0) {
     const char* e = getenv("B200SCN_GPL_WARPS");
-    large_warps = e ? atoi(e) : kLargeWarps;
-    if (large_warps < 1 || large_warps > kLargeWarps) large_warps = kLargeWarps;
+    v = e ? atoi(e) : kLargeWarps;
+    if (v < 1 || v > kLargeWarps) v = kLargeWarps;
   }
-  int warps = pl.wsmem ? large_warps : 8;
-  while (warps > 1 && fixed + warps * acc_bytes(R, pl.MT) > (size_t)kMaxSmem) --warps;
-  if (fixed + warps * acc_bytes(R, pl.MT) > (size_t)kMaxSmem) return pl;
-  pl.warps = warps;
-  pl.smem = fixed + warps * acc_bytes(R, pl.MT);
-  int cps = (int)((size_t)(227 * 1024) / (pl.smem + 1024));
-  if (cps > 2048 / (warps * 32)) cps = 2048 / (warps * 32);
-  if (cps > 8) cps = 8;
-  if (cps < 1) cps = 1;
-  pl.ctas_per_sm = cps;
-  pl.ok = true;
-  return pl;
+  return v;
 }
 
-template <int Q, int MT, bool WSMEM, bool X3, int R>
-int launch_gpl(const GplParams& p, const GPlan& pl, cudaStream_t st) {
+// ---- large inputs: k_conv_gpl, one warp per tile, weights resident in shared memory ---------------
+template <int Q, int MT, bool X3>
+int launch_large(GplParams p, int passes, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, WSMEM, X3, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, true, X3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kMaxSmem));
     configured = true;
   }
-  const int64_t tiles = cdiv(p.n_cap, R);
-  int64_t gx = pl.split ? tiles : cdiv(tiles, pl.warps);
-  int64_t gmax = WSMEM ? ((int64_t)sm_count() * pl.ctas_per_sm) / pl.passes : (int64_t)sm_count() * pl.ctas_per_sm * 4;
+  const size_t fixed = w_smem_bytes(p.K, 16 * Q, MT, X3);
+  int warps = large_warps();
+  while (warps > 1 && fixed + warps * acc_bytes(128, MT) > (size_t)kMaxSmem) --warps;
+  p.warps = warps;
+  p.split = 0;
+  const int64_t tiles = cdiv(p.n_cap, 128);
+  int64_t gx = cdiv(tiles, warps);
+  int64_t gmax = sm_count() / passes;
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)pl.passes);
-  k_conv_gpl<Q, MT, WSMEM, X3, R><<<grid, pl.warps * 32, pl.smem, st>>>(p);
+  dim3 grid((unsigned)gx, (unsigned)passes);
+  k_conv_gpl<Q, MT, true, X3, 128><<<grid, warps * 32, fixed + warps * acc_bytes(128, MT), st>>>(p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
 }
 
-template <int Q, int MT, bool X3>
-int launch_gpl_qmx(const GplParams& p, const GPlan& pl, int R, cudaStream_t st) {
-  if (pl.wsmem) return launch_gpl<Q, MT, true, X3, 128>(p, pl, st);
-  return R == 128 ? launch_gpl<Q, MT, false, X3, 128>(p, pl, st) : launch_gpl<Q, MT, false, X3, 64>(p, pl, st);
+template <int Q>
+int launch_large_q(const GplParams& p, int MT, int passes, int x3, cudaStream_t st) {
+  if (MT == 1) return x3 ? launch_large<Q, 1, true>(p, passes, st) : launch_large<Q, 1, false>(p, passes, st);
+  return x3 ? launch_large<Q, 2, true>(p, passes, st) : launch_large<Q, 2, false>(p, passes, st);
 }
 
-template <int Q>
-int launch_gpl_q(const GplParams& p, const GPlan& pl, int R, int x3, cudaStream_t st) {
-  if (pl.MT == 1) return x3 ? launch_gpl_qmx<Q, 1, true>(p, pl, R, st) : launch_gpl_qmx<Q, 1, false>(p, pl, R, st);
-  return x3 ? launch_gpl_qmx<Q, 2, true>(p, pl, R, st) : launch_gpl_qmx<Q, 2, false>(p, pl, R, st);
+// ---- small inputs: k_conv_gpl_small ---------------------------------------------------------------
+template <int MT, bool X3, int R, bool PACKED>
+int launch_small(GplParams p, int passes, cudaStream_t st) {
+  static thread_local bool configured = false;
+  static int small_warps = 0;  // B200SCN_GPL_SMALL_WARPS (A/B runs)
+  if (small_warps == 0) {
+    const char* e = getenv("B200SCN_GPL_SMALL_WARPS");
+    small_warps = e ? atoi(e) : 16;
+    if (small_warps < 1 || small_warps > 16) small_warps = 16;
+  }
+  int warps = small_warps;
+  while (warps > 4 && warps * acc_bytes(R, MT) > (size_t)112 * 1024) warps >>= 1;  // two CTAs per SM
+  const size_t smem = warps * acc_bytes(R, MT);
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl_small<MT, X3, R, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(16 * acc_bytes(R, MT) > (size_t)kMaxSmem ? (size_t)kMaxSmem : 16 * acc_bytes(R, MT))));
+    configured = true;
+  }
+  p.warps = warps;
+  p.split = 1;
+  int64_t gx = cdiv(p.n_cap, R);
+  const int64_t gmax = (int64_t)sm_count() * 16;
+  if (gx > gmax) gx = gmax;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)passes);
+  k_conv_gpl_small<MT, X3, R, PACKED><<<grid, warps * 32, smem, st>>>(p);
+  count_launches(1);
+  B200_CHECK_LAUNCH("conv_gpl_small");
+  return 0;
+}
+
+template <int MT, bool X3, bool PACKED>
+int launch_small_rp(const GplParams& p, int passes, int R, cudaStream_t st) {
+  switch (R) {
+    case 32: return launch_small<MT, X3, 32, PACKED>(p, passes, st);
+    case 64: return launch_small<MT, X3, 64, PACKED>(p, passes, st);
+    default: return launch_small<MT, X3, 128, PACKED>(p, passes, st);
+  }
+}
+template <int MT, bool X3>
+int launch_small_r(const GplParams& p, int passes, int R, cudaStream_t st) {
+  return p.Wp ? launch_small_rp<MT, X3, true>(p, passes, R, st) : launch_small_rp<MT, X3, false>(p, passes, R, st);
+}
+
+// ---- weight packing -------------------------------------------------------------------------------
+// job = int64[10]: {W, out, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0}; out[((((k' Q + q) 2 + h) CoT + mt) 32 + lane) 4 + r]
+// with the fragment maps of k_conv_gpl: lane = 4 (co & 7) + ((ci & 15) >> 2), h = (ci & 3) >> 1,
+// r = 2 ((co >> 3) & 1) + (ci & 1), k' = kflip ? K-1-k : k.
+__global__ void k_pack_weights(const int64_t* __restrict__ jobs) {
+  const int64_t* j = jobs + (size_t)blockIdx.y * 10;
+  const float* W = reinterpret_cast<const float*>(j[0]);
+  float* out = reinterpret_cast<float*>(j[1]);
+  const int K = (int)j[2], Cin = (int)j[3], Cout = (int)j[4];
+  const int64_t w_sk = j[5], w_si = j[6], w_so = j[7];
+  const int kflip = (int)j[8];
+  const int Q = Cin >> 4, CoT = Cout >> 4;
+  const bool co_fast = (w_so == 1);
+  const int fast_n = co_fast ? Cout : Cin, slow_n = co_fast ? Cin : Cout;
+  const int64_t total = (int64_t)K * Cin * Cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e % fast_n);
+    const int64_t rest = e / fast_n;
+    const int sl = (int)(rest % slow_n);
+    const int k = (int)(rest / slow_n);
+    const int ci = co_fast ? sl : f, co = co_fast ? f : sl;
+    const float v = __ldg(W + k * w_sk + ci * w_si + co * w_so);
+    const int kk = kflip ? (K - 1 - k) : k;
+    const int q = ci >> 4, c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3, h = rem >> 1;
+    const int mt = co >> 4, odd = (co >> 3) & 1, gg = co & 7;
+    out[((((size_t)(kk * Q + q) * 2 + h) * CoT + mt) * 32 + gg * 4 + tt) * 4 + odd * 2 + (rem & 1)] = v;
+  }
 }
 
 }  // namespace
@@ -536,30 +751,51 @@ int launch_gpl_q(const GplParams& p, const GPlan& pl, int R, int x3, cudaStream_
 
 using namespace b200scn;
 
-/* tile rows the library recommends for a level of n_cap rows */
-extern "C" int b200scn_gpl_tile_rows(int64_t n_cap) { return n_cap >= 12288 ? 128 : 64; }
+/* tile rows the library recommends for a level of n rows */
+extern "C" int b200scn_gpl_tile_rows(int64_t n) { return n >= 12288 ? 128 : (n >= 5120 ? 64 : 32); }
 
-/* upper bound of the number of groups for n_cap rows (static regime allocation) */
+/* upper bound of the number of groups for n_cap rows (static regime allocation, fixed-stride lists) */
 extern "C" int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows) {
   const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
   return tiles * (int64_t)K * (tile_rows / 16);
 }
 
 extern "C" int64_t b200scn_gpl_scratch_bytes(int64_t n_cap) {
-  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, 64);
+  const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, 32);
   return (tiles + 8) * 4 + (cdiv(tiles, 1024) + 16) * 4 + 256;
 }
 
+template <bool FILL>
+static void launch_build(int tile_rows, int grid, int threads, cudaStream_t st, const int32_t* table, int64_t ld,
+                         const int32_t* parent, const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev,
+                         int32_t* tile_cnt, const int32_t* tile_off, int32_t* tile_beg_out, int4* rec, int64_t cap) {
+  switch (tile_rows) {
+    case 32:
+      k_gpl_build<FILL, 32><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
+                                                      tile_beg_out, rec, cap);
+      break;
+    case 64:
+      k_gpl_build<FILL, 64><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
+                                                      tile_beg_out, rec, cap);
+      break;
+    default:
+      k_gpl_build<FILL, 128><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
+                                                       tile_beg_out, rec, cap);
+  }
+}
+
 /* stage 0: tile_off[tiles + 1] (exclusive scan of the per-tile group counts) and total_dev[1].
- * stage 1: fill g_rec[cap_groups * 8] (int4 records) using tile_off. */
+ * stage 1: fill g_rec[cap_groups * 8] (int4 records) using tile_off.
+ * stage 2: single pass with fixed-stride slots (cap_groups >= b200scn_gpl_max_groups): writes tile_off[tiles]
+ *          (begin) and tile_end[tiles]; no scan, nothing to read back -- the static (CUDA graph) regime. */
 extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent,
                                  const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int tile_rows,
-                                 int32_t* tile_off, int32_t* total_dev, void* g_rec, int64_t cap_groups, void* scratch,
-                                 int64_t scratch_bytes, void* stream) {
+                                 int32_t* tile_off, int32_t* tile_end, int32_t* total_dev, void* g_rec,
+                                 int64_t cap_groups, void* scratch, int64_t scratch_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= 64, "gpl_build: K must be 1..64");
-  B200_CHECK_ARG(tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 64 or 128");
-  B200_CHECK_ARG(scratch_bytes >= b200scn_gpl_scratch_bytes(n_cap), "gpl_build: scratch too small");
+  B200_CHECK_ARG(tile_rows == 32 || tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 32, 64 or 128");
+  B200_CHECK_ARG(stage == 2 || scratch_bytes >= b200scn_gpl_scratch_bytes(n_cap), "gpl_build: scratch too small");
   const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(scratch);
   int32_t* bsums = tile_cnt + tiles + 8;
@@ -571,62 +807,82 @@ extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, co
   int4* rec = reinterpret_cast<int4*>(g_rec);
   if (stage == 0) {
     B200_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(tiles + 8) * 4, st));
-    if (n_cap > 0) {
-      if (tile_rows == 128)
-        k_gpl_build<false, 128><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
-                                                                  nullptr, nullptr, 0);
-      else
-        k_gpl_build<false, 64><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
-                                                                 nullptr, nullptr, 0);
-    }
+    if (n_cap > 0)
+      launch_build<false>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
+                          nullptr, nullptr, nullptr, 0);
     // exclusive scan over all `tiles` counts (tiles beyond the live ones hold 0)
     if (int rc = scan_i32_public(tile_cnt, tile_off, tiles, nullptr, total_dev, tile_off, bsums, st)) return rc;
     count_launches(4);
+  } else if (stage == 1) {
+    if (n_cap > 0)
+      launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
+                         tile_off, nullptr, rec, cap_groups);
+    count_launches(1);
   } else {
-    if (n_cap > 0) {
-      if (tile_rows == 128)
-        k_gpl_build<true, 128><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
-                                                                 tile_off, rec, cap_groups);
-      else
-        k_gpl_build<true, 64><<<(int)grid, warps * 32, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
-                                                                tile_off, rec, cap_groups);
-    }
+    B200_CHECK_ARG(tile_end != nullptr, "gpl_build: stage 2 needs tile_end");
+    B200_CHECK_ARG(cap_groups >= b200scn_gpl_max_groups(n_cap, K, tile_rows), "gpl_build: stage 2 needs worst-case capacity");
+    if (n_cap > 0)
+      launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_end,
+                         nullptr, tile_off, rec, cap_groups);
     count_launches(1);
   }
   B200_CHECK_LAUNCH("gpl_build");
   return 0;
 }
 
-extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
-                                int kflip, int tile_rows, const int32_t* tile_off, const void* g_rec, int K,
-                                int64_t n_out_cap, const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo,
-                                int accumulate, int math_mode, void* stream) {
+extern "C" int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_jobs <= 0) return 0;
+  B200_CHECK_ARG(n_jobs <= 65535, "pack_weights: too many jobs");
+  int64_t gx = cdiv(max_elems < 1 ? 1 : max_elems, 256 * 4);
+  if (gx > 64) gx = 64;
+  k_pack_weights<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(jobs_dev);
+  count_launches(1);
+  B200_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
+                                int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
+                                const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int Cin,
+                                int Cout, float* out, int64_t ldo, int accumulate, int math_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16, "conv_gpl: channels must be multiples of 16");
   B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "conv_gpl: tensor-core math modes only");
   B200_CHECK_ARG(ldi % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv_gpl: input rows must be 16-byte aligned");
-  B200_CHECK_ARG(tile_rows == 64 || tile_rows == 128, "conv_gpl: tile_rows must be 64 or 128");
+  B200_CHECK_ARG(tile_rows == 32 || tile_rows == 64 || tile_rows == 128, "conv_gpl: tile_rows must be 32, 64 or 128");
   const int64_t lim = (1ll << 31) - 1;
   B200_CHECK_ARG(ldi < lim && ldo < lim && (int64_t)K * Cin * Cout < lim, "conv_gpl: stride out of 32-bit range");
   if (n_out_cap == 0) return 0;
   const int x3 = math_mode == B200SCN_MATH_TF32X3 ? 1 : 0;
-  for (int c0 = 0; c0 < Cin; c0 += 64) {
-    const int cc = Cin - c0 < 64 ? Cin - c0 : 64;
-    GPlan pl = plan_gpl(K, cc, Cout, n_out_cap, x3, tile_rows);
-    B200_CHECK_ARG(pl.ok, "conv_gpl: unsupported shape Cin=%d Cout=%d K=%d", Cin, Cout, K);
-    GplParams p;
-    p.in = in + c0; p.ldi = (int)ldi; p.W = W + (int64_t)c0 * w_si; p.w_sk = (int)w_sk; p.w_si = (int)w_si;
-    p.w_so = (int)w_so; p.kflip = kflip; p.tile_off = tile_off; p.g_rec = reinterpret_cast<const int4*>(g_rec);
-    p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out;
-    p.ldo = (int)ldo; p.accumulate = (c0 > 0) ? 1 : accumulate; p.warps = pl.warps; p.split = pl.split; p.ones = 0xffffffffu;
-    int rc;
-    switch (pl.Q) {
-      case 1: rc = launch_gpl_q<1>(p, pl, tile_rows, x3, st); break;
-      case 2: rc = launch_gpl_q<2>(p, pl, tile_rows, x3, st); break;
-      case 3: rc = launch_gpl_q<3>(p, pl, tile_rows, x3, st); break;
-      default: rc = launch_gpl_q<4>(p, pl, tile_rows, x3, st); break;
+  const int cot = Cout / 16;
+  GplParams p;
+  p.Wp = Wp; p.cot = Cout / 16;
+  p.in = in; p.ldi = (int)ldi; p.W = W; p.w_sk = (int)w_sk; p.w_si = (int)w_si; p.w_so = (int)w_so; p.kflip = kflip;
+  p.tile_off = tile_off; p.tile_end = tile_end; p.g_rec = reinterpret_cast<const int4*>(g_rec); p.Q = Cin / 16;
+  p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = accumulate;
+  p.warps = 8; p.split = 1; p.ones = 0xffffffffu;
+
+  // large inputs (enough 128-row tiles to give every SM a CTA of one-tile warps) with scanned lists and
+  // a weight slice that fits in shared memory next to >= 12 accumulators: k_conv_gpl
+  const bool large = tile_rows == 128 && tile_end == nullptr && Cin <= 64 && n_out_cap >= (int64_t)128 * 8 * sm_count();
+  if (large) {
+    int MT = 0;
+    for (int mt = 2; mt >= 1; --mt)
+      if (cot % mt == 0 && w_smem_bytes(K, Cin, mt, x3) + 12 * acc_bytes(128, mt) <= (size_t)kMaxSmem) { MT = mt; break; }
+    if (MT) {
+      switch (p.Q) {
+        case 1: return launch_large_q<1>(p, MT, cot / MT, x3, st);
+        case 2: return launch_large_q<2>(p, MT, cot / MT, x3, st);
+        case 3: return launch_large_q<3>(p, MT, cot / MT, x3, st);
+        default: return launch_large_q<4>(p, MT, cot / MT, x3, st);
+      }
     }
-    if (rc) return rc;
   }
-  return 0;
+  // small inputs: narrow passes unless the tiles alone already cover the SMs twice
+  const int64_t tiles = cdiv(n_out_cap, tile_rows);
+  const int MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
+  if (MT == 1)
+    return x3 ? launch_small_r<1, true>(p, cot, tile_rows, st) : launch_small_r<1, false>(p, cot, tile_rows, st);
+  return x3 ? launch_small_r<2, true>(p, cot / 2, tile_rows, st) : launch_small_r<2, false>(p, cot / 2, tile_rows, st);
 }

@@ -19,10 +19,20 @@ overlap_wgrad = False
 use_gpl = not os.environ.get("B200SCN_NO_GPL")
 # levels with fewer rows keep the in-kernel listing (conv_pairs.cu, offset-split CTAs): building the lists
 # costs more than it saves when one launch is a few microseconds
-gpl_min_rows = int(os.environ.get("B200SCN_GPL_MIN_ROWS", "65536"))
+gpl_min_rows = int(os.environ.get("B200SCN_GPL_MIN_ROWS", "0"))
 
 # rows per tile of the grouped pair lists (64 / 128); None = the library's recommendation for the level size
 gpl_tile_rows = int(os.environ["B200SCN_GPL_TILE_ROWS"]) if os.environ.get("B200SCN_GPL_TILE_ROWS") else None
+
+# True: convolutions over grouped pair lists read a fragment-ordered copy of the weights (functional.packed_weights)
+pack_weights = not os.environ.get("B200SCN_NO_PACK")
+
+# static regime: tile rows per spatial size.  A level's capacity says nothing about how many rows it really
+# has, so the trainer calibrates this once on a real event (Trainer._calibrate_tiles)
+gpl_tile_rows_by_size = {}
+
+# static regime: levels below this capacity build their pair lists in one pass into fixed-stride slots
+gpl_fixed_stride_max_rows = 128 * 8 * 148
 
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None

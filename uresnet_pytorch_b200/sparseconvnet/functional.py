@@ -81,12 +81,65 @@ def _gpl_ok(gpl, x, Cin, Cout, math):
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
 
 
+# Fragment-ordered weight copies (b200scn_pack_weights), one per (weight storage, direction).  An entry is
+# re-packed when the weight's version counter moved; a trainer that steps the optimiser inside a CUDA graph
+# calls repack_all() right after it, so the (captured) forward never finds a stale copy.
+_pack_cache = {}
+_pack_all_jobs = None
+
+
+def _pack_entry(W3, Cin, Cout, w_si, w_so, kflip):
+    key = (W3.data_ptr(), w_so == 1, kflip)
+    ent = _pack_cache.get(key)
+    if ent is None or ent["shape"] != tuple(W3.shape) or ent["device"] != W3.device:
+        global _pack_all_jobs
+        K = W3.shape[0]
+        buf = torch.empty(K * Cin * Cout, dtype=torch.float32, device=W3.device)
+        job = torch.tensor([W3.data_ptr(), buf.data_ptr(), K, Cin, Cout, W3.shape[1] * W3.shape[2], w_si, w_so, kflip,
+                            0], dtype=torch.int64).to(W3.device)
+        ent = dict(shape=tuple(W3.shape), device=W3.device, buf=buf, job=job, version=None, W=W3,
+                   elems=K * Cin * Cout)
+        _pack_cache[key] = ent
+        _pack_all_jobs = None
+    return ent
+
+
+def packed_weights(W3, Cin, Cout, w_si, w_so, kflip):
+    """Device pointer of the fragment-ordered copy of W3 for the direction (Cin, Cout, w_si, w_so, kflip)."""
+    ent = _pack_entry(W3, Cin, Cout, w_si, w_so, kflip)
+    if ent["version"] != W3._version:
+        _lib.call("b200scn_pack_weights", ent["job"].data_ptr(), 1, ent["elems"], _stream())
+        ent["version"] = W3._version
+    return ent["buf"].data_ptr()
+
+
+def repack_all():
+    """Refresh every cached copy with ONE launch (after an optimiser step / a state-dict load)."""
+    global _pack_all_jobs
+    if not _pack_cache:
+        return
+    ents = list(_pack_cache.values())
+    if _pack_all_jobs is None:
+        _pack_all_jobs = torch.cat([e["job"] for e in ents])
+    _lib.call("b200scn_pack_weights", _pack_all_jobs.data_ptr(), len(ents), max(e["elems"] for e in ents), _stream())
+    for e in ents:
+        e["version"] = e["W"]._version
+
+
+def clear_pack_cache():
+    global _pack_all_jobs
+    _pack_cache.clear()
+    _pack_all_jobs = None
+
+
 def _conv_gpl(x, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
     """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
-    _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), W3.shape[1] * W3.shape[2], w_si, w_so,
-              kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), gpl["g_rec"].data_ptr(), K, n_out, n_out_dev,
+    Wp = packed_weights(W3, Cin, Cout, w_si, w_so, kflip) if config.pack_weights else None
+    _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
+              kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
+              n_out, n_out_dev,
               Cin, Cout, out.data_ptr(), out.stride(0), 0, math, _stream())
     return out
 

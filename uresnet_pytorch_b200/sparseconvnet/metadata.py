@@ -165,35 +165,46 @@ class Metadata(object):
         return rules
 
     # -- grouped pair lists (tensor-core convolution input) ------------------------------------
-    def _build_gpl(self, lv, table, parent, kofs, K):
+    def _build_gpl(self, lv, table, parent, kofs, K, size_key=None):
         """Pair list over the rows of `lv` (the OUTPUT rows of the convolution that will use it)."""
         L = _lib.load()
         rows = lv.rows
         nd = self.n_dev_ptr(lv)
-        tile = config.gpl_tile_rows or L.b200scn_gpl_tile_rows(max(rows, 1))
+        tile = (config.gpl_tile_rows or (self.static and config.gpl_tile_rows_by_size.get(size_key))
+                or L.b200scn_gpl_tile_rows(max(rows, 1)))
         tiles = max((max(rows, 1) + tile - 1) // tile, 1)
         dev = self.device
         tile_off = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
+        tab = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
+               nd, tile)
+        if self.static and rows < config.gpl_fixed_stride_max_rows:
+            # static regime: one pass into fixed-stride slots, nothing to scan or read back
+            cap = L.b200scn_gpl_max_groups(max(rows, 1), K, tile)
+            tile_end = torch.empty(tiles, dtype=torch.int32, device=dev)
+            g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)
+            _lib.call("b200scn_gpl_build", 2, *tab, _lib.ptr(tile_off), _lib.ptr(tile_end), None, _lib.ptr(g_rec), cap,
+                      None, 0, _stream())
+            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile)
         total = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        args = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
-                nd, tile, _lib.ptr(tile_off), _lib.ptr(total))
-        _lib.call("b200scn_gpl_build", 0, *args, None, 0, _lib.ptr(scratch), nbytes, _stream())
+        _lib.call("b200scn_gpl_build", 0, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), None, 0, _lib.ptr(scratch),
+                  nbytes, _stream())
         if self.static:
             cap = L.b200scn_gpl_max_groups(max(rows, 1), K, tile)
         else:
             cap = max(int(total.item()), 1)
         g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)  # [cap][8] int4 records
-        _lib.call("b200scn_gpl_build", 1, *args, _lib.ptr(g_rec), cap, _lib.ptr(scratch), nbytes, _stream())
-        return dict(tile_off=tile_off, g_rec=g_rec, K=K, tile_rows=tile)
+        _lib.call("b200scn_gpl_build", 1, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), _lib.ptr(g_rec), cap,
+                  _lib.ptr(scratch), nbytes, _stream())
+        return dict(tile_off=tile_off, tile_end=None, g_rec=g_rec, K=K, tile_rows=tile)
 
     def subm_gpl(self, spatial_size, filter_size):
         lv = self.level(spatial_size)
         key = ("subm", filter_size)
         if key not in lv.gpl:
             nbr = self.subm_table(spatial_size, filter_size)
-            lv.gpl[key] = self._build_gpl(lv, nbr, None, None, filter_size ** self.dimension)
+            lv.gpl[key] = self._build_gpl(lv, nbr, None, None, filter_size ** self.dimension, tuple(spatial_size))
         return lv.gpl[key]
 
     def strided_gpl(self, in_size, out_size, stride):
@@ -202,9 +213,9 @@ class Metadata(object):
         fine, coarse = self.level(in_size), self.level(out_size)
         K = stride ** self.dimension
         if ("child", stride) not in coarse.gpl:
-            coarse.gpl[("child", stride)] = self._build_gpl(coarse, rules["child"], None, None, K)
+            coarse.gpl[("child", stride)] = self._build_gpl(coarse, rules["child"], None, None, K, tuple(out_size))
         if ("parent", stride) not in fine.gpl:
-            fine.gpl[("parent", stride)] = self._build_gpl(fine, None, rules["parent"], rules["kofs"], K)
+            fine.gpl[("parent", stride)] = self._build_gpl(fine, None, rules["parent"], rules["kofs"], K, tuple(in_size))
         return coarse.gpl[("child", stride)], fine.gpl[("parent", stride)]
 
     # -- introspection (tests, debugging) ---------------------------------------------------

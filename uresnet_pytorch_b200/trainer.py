@@ -123,6 +123,7 @@ class Trainer(object):
                         scn_functional.join_side_streams()
                     self._allreduce_grads()
                     self.opt.step()
+                    scn_functional.repack_all()  # fragment-ordered weight copies follow the new weights
         return loss, acc, logits
 
     def _masked_loss(self, logits, data, lab, w):
@@ -138,9 +139,31 @@ class Trainer(object):
         return (s / safe).sum(), (h / safe).sum()
 
     # ------------------------------------------------------------------------------------
+    def _calibrate_tiles(self):
+        """Row counts of the U-Net levels of the event in the staging buffer (eager rulebook build, one
+        host read-back per level) -> tile rows of every level's grouped pair lists in the captured graph."""
+        from . import _lib
+        from .sparseconvnet.metadata import Metadata
+        n = int(self.h_n[0])
+        if n <= 0:
+            return
+        D = self.flags.DATA_DIM
+        L = _lib.load()
+        md = Metadata(D)
+        size = (int(self.flags.SPATIAL_SIZE),) * D
+        lv = md.set_input(self.d_data[:n, :D + 1], size)
+        hints = {size: L.b200scn_gpl_tile_rows(max(lv.n, 1))}
+        for _ in range(int(self.flags.URESNET_NUM_STRIDES) - 1):
+            out = tuple((v - 2) // 2 + 1 for v in size)
+            md.down_rules(size, out, 2)
+            hints[out] = L.b200scn_gpl_tile_rows(max(md.level(out).n, 1))
+            size = out
+        scn.config.gpl_tile_rows_by_size = hints
+
     def _capture(self):
         """Warm up on a side stream, then capture the whole step into one CUDA graph."""
         valid = None
+        self._calibrate_tiles()
 
         def step():
             nonlocal valid
@@ -172,6 +195,7 @@ class Trainer(object):
         self._graph = g
         # restore the pre-warm-up weights / BN stats and reset Adam
         self.net.load_state_dict(state)
+        scn_functional.repack_all()
         if self.train:
             for st in self.opt.state.values():
                 for k, v in st.items():
