@@ -253,7 +253,7 @@ def run_b200(args):
                   URESNET_NUM_STRIDES=CONFIG["uns"], NUM_CLASS=CONFIG["nc"])
     pool = make_pool(args, rank)
     cap = max(len(d) for d, _ in pool)
-    cap = ((cap + cap // 8 + 4095) // 4096) * 4096
+    cap = ((cap + cap // 8 + 4095) // 4096) * 4096 * int(os.environ.get("B200SCN_BENCH_CAP_MULT", "1"))
     graph = not args.no_graph
     trainer = Trainer(flags, lr=1e-3, graph=graph, capacity=cap if graph else None,
                       events_per_step=args.events_per_gpu, math_mode=math_mode, seed=0,

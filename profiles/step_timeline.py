@@ -32,7 +32,7 @@ class A(object):
 
 
 pool = bench.make_pool(A, 0)
-cap = ((max(len(d) for d, _ in pool) * 9 // 8 + 4095) // 4096) * 4096
+cap = ((max(len(d) for d, _ in pool) * 9 // 8 + 4095) // 4096) * 4096 * int(os.environ.get("B200SCN_BENCH_CAP_MULT", "1"))
 tr = Trainer(flags, graph=True, capacity=cap, events_per_step=1, math_mode=mode, overlap_wgrad=not a.no_overlap)
 for i in range(4):
     tr.train_step(*pool[i % 4])

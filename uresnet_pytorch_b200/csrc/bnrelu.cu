@@ -138,6 +138,8 @@ __global__ void k_bn_apply_train(const float* __restrict__ x, int64_t ldx, int64
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
+  // grids are sized by the row capacity: CTAs without a live row leave before the fold (CTA 0 publishes)
+  if (blockIdx.x != 0 && (int64_t)blockIdx.x * RL >= n) return;
   const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
     float N = 0.f, M = 0.f, S = 0.f;
@@ -240,6 +242,7 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const f
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
+  if (blockIdx.x != 0 && (int64_t)blockIdx.x * RL >= n) return;
   const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
     float a1 = 0.f, a2 = 0.f;

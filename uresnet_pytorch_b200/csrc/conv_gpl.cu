@@ -693,8 +693,11 @@ int launch_small(GplParams p, int passes, cudaStream_t st) {
   }
   p.warps = warps;
   p.split = 1;
+  // CTAs loop over tiles: a grid a few waves deep, not one CTA per tile of the row CAPACITY (in the
+  // CUDA-graph regime most of those would find no live tile and only cost launch overhead)
   int64_t gx = cdiv(p.n_cap, R);
-  const int64_t gmax = (int64_t)sm_count() * 16;
+  int64_t gmax = cdiv((int64_t)sm_count() * 4, passes);
+  if (gmax < sm_count()) gmax = sm_count();
   if (gx > gmax) gx = gmax;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)passes);

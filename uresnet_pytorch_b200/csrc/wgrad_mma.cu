@@ -60,16 +60,32 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// TPW = (ci, co) mma tiles per warp.  grid = (K, row chunks, column splits)
+// rows per partial block when n live rows are split over `parts` CTAs (multiple of 32), and how many of
+// those CTAs own at least one row
+__host__ __device__ __forceinline__ int wg_rows_per_part(int n, int parts) {
+  const int per = (n + parts - 1) / parts;
+  return ((per + 31) / 32) * 32;
+}
+__host__ __device__ __forceinline__ int wg_live_parts(int n, int parts) {
+  const int per = wg_rows_per_part(n, parts);
+  const int live = per > 0 ? (n + per - 1) / per : 0;
+  return live < 1 ? 1 : (live > parts ? parts : live);
+}
+
+// TPW = (ci, co) mma tiles per warp.  grid = (K, row parts, column splits)
 template <int TPW>
 __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int k = blockIdx.x;
-  const int r_begin = blockIdx.y * p.rows_per_cta;
-  const int live_chunks = max(1, min((int)gridDim.y, (n + p.rows_per_cta - 1) / p.rows_per_cta));
+  // The live rows are split evenly over the gridDim.y CTAs of this offset (contiguous ranges, a multiple
+  // of 32 rows); a CTA walks its range in sub-chunks of rows_per_cta rows and keeps its accumulators in
+  // registers across them, so the grid -- and the number of partial blocks to fold -- does not grow with
+  // the row CAPACITY of the buffers (profiles/README.md: capacity-sized grids cost ~1 ms per step).
+  const int per_cta = wg_rows_per_part(n, (int)gridDim.y);
+  const int live_chunks = wg_live_parts(n, (int)gridDim.y);
   if ((int)blockIdx.y >= live_chunks) return;
-  const int r_end = min(n, r_begin + p.rows_per_cta);
+  const int cta_begin = blockIdx.y * per_cta, cta_end = min(n, cta_begin + per_cta);
   const int cb0 = blockIdx.z * p.cb_per_z;                 // first output channel of this split
   const int Cbz = min(p.cb_per_z, p.Cb - cb0);             // output channels handled here
   const int Ca = p.Ca;
@@ -84,6 +100,17 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
   float* stage_base = reinterpret_cast<float*>(wsum + 16);
   const int stage_floats = kBatch * (sa + sb);
 
+  const int MT = Ca >> 4, NT8 = Cbz >> 3;
+  const int T = MT * NT8;
+  float acc[TPW][4];
+#pragma unroll
+  for (int i = 0; i < TPW; ++i)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+  const int qa = Ca >> 2, qb = Cbz >> 2;  // 16 B chunks per row
+
+  for (int r_begin = cta_begin; r_begin < cta_end; r_begin += p.rows_per_cta) {
+  const int r_end = min(cta_end, r_begin + p.rows_per_cta);
   // ---- (1) compact the valid pairs of [r_begin, r_end) in row order ---------------------------
   int total = 0;
   for (int c0 = r_begin; c0 < r_end; c0 += nthr) {
@@ -106,15 +133,6 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
     __syncthreads();
   }
 
-  const int MT = Ca >> 4, NT8 = Cbz >> 3;
-  const int T = MT * NT8;
-  float acc[TPW][4];
-#pragma unroll
-  for (int i = 0; i < TPW; ++i)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
-
-  const int qa = Ca >> 2, qb = Cbz >> 2;  // 16 B chunks per row
   auto issue = [&](int batch, int stage) {
     float* As = stage_base + stage * stage_floats;
     float* Bs = As + kBatch * sa;
@@ -179,6 +197,8 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
     __syncthreads();  // stage (b & 1) is refilled by the next iteration's issue
   }
   cp_async_wait<0>();
+  __syncthreads();  // the pair lists are rewritten by the next sub-chunk
+  }
 
   // ---- (4) partial block -> scratch[(chunk * K + k)][Ca][Cb] ------------------------------------
   float* dst = p.part + ((int64_t)blockIdx.y * p.K + k) * Ca * p.Cb;
@@ -228,8 +248,8 @@ __global__ void k_wgrad_fold(const float* __restrict__ part, int64_t elems, int 
                              int64_t n_cap, const int32_t* __restrict__ n_dev, float* __restrict__ dW,
                              int accumulate) {
   const int n = live_rows(n_dev, n_cap);
-  int live = (n + rows_per_cta - 1) / rows_per_cta;
-  if (live > nchunks) live = nchunks;
+  const int live = n > 0 ? wg_live_parts(n, nchunks) : 0;
+  (void)rows_per_cta;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < elems; e += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int c = 0; c < live; ++c) s += part[(int64_t)c * elems + e];
@@ -264,20 +284,23 @@ WgPlan wg_plan(int64_t n_cap, int K, int Ca, int Cb) {
   int tpw_pow = 1;
   while (tpw_pow < tpw) tpw_pow <<= 1;
   if (tpw_pow > 16) return pl;
-  // row range per CTA: at most 128 chunks (scratch size, fold cost), at least 256 rows
-  static int max_chunks = 0;  // tunable for A/B runs: B200SCN_WG_CHUNKS
-  if (max_chunks == 0) {
-    const char* e = getenv("B200SCN_WG_CHUNKS");
-    max_chunks = e ? atoi(e) : 128;
-    if (max_chunks < 1) max_chunks = 1;
-    if (max_chunks > 128) max_chunks = 128;
+  // sub-chunk of rows compacted at a time (pair lists in shared memory), and the number of row parts
+  // (= CTAs per offset and column split = partial blocks): enough to cover the SMs about twice, never
+  // more than one part per 256 rows of capacity
+  static int parts_target = 0;  // tunable for A/B runs: B200SCN_WG_PARTS (CTAs aimed at, default 4 x SMs)
+  if (parts_target == 0) {
+    const char* e = getenv("B200SCN_WG_PARTS");
+    parts_target = e ? atoi(e) : 4 * sm_count();
+    if (parts_target < 1) parts_target = 1;
   }
-  int64_t rows = cdiv(n_cap < 1 ? 1 : n_cap, max_chunks);
-  if (rows < 256) rows = 256;
-  rows = cdiv(rows, 256) * 256;
-  if (rows > 16384) rows = 16384;  // pair lists live in shared memory
+  const int64_t rows = 1024;
+  int64_t parts = cdiv(parts_target, (int64_t)K * z);
+  const int64_t max_parts = cdiv(n_cap < 1 ? 1 : n_cap, 256);
+  if (parts > max_parts) parts = max_parts;
+  if (parts > 128) parts = 128;
+  if (parts < 1) parts = 1;
   pl.rows_per_cta = (int)rows;
-  pl.nchunks = (int)cdiv(n_cap < 1 ? 1 : n_cap, rows);
+  pl.nchunks = (int)parts;
   pl.zsplits = z;
   pl.cb_per_z = cbz;
   pl.warps = warps;
