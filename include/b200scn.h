@@ -227,6 +227,23 @@ int64_t b200scn_colsum_scratch_bytes(int C);
 int b200scn_colsum(const float* x, int64_t ldx, int64_t n, int C, float* out, void* scratch, int64_t scratch_bytes,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (vii) fused segmentation head + loss: the Linear(m -> nc) of
+ * /root/reference/uresnet/models/uresnet_sparse.py:25,36 and SegmentationLoss.forward (:44-82) --
+ * per-event mean cross-entropy (optionally pixel-weighted) summed over events, per-event accuracy summed
+ * over events -- plus the whole backward of that chain for an upstream gradient of 1.
+ * feat [n, m] = OutputLayer rows; W [nc, m], bias [nc] (torch.nn.Linear layout); label [n] (float class ids,
+ * as the reference ships them); ids = the sample-id column (dtype code as for b200scn_input_build, element
+ * stride ld_ids); nb = number of events a sample id may name (ids outside [0, nb) are ignored).
+ * Outputs: loss_acc[2] = {total_loss, total_acc}; optional logits [n, nc]; optional (training) dfeat [n, m],
+ * dW [nc, m], db [nc].  Deterministic (integer counting pass, fixed-order partial sums). */
+int64_t b200scn_head_loss_scratch_bytes(int64_t n_cap, int m, int nc, int nb);
+int b200scn_head_loss(const float* feat, int64_t ldf, const float* W, const float* bias, const float* label,
+                      int64_t ld_label, const float* pix_w, int64_t ld_pw, const void* ids, int id_dtype,
+                      int64_t ld_ids, int64_t n_cap, const int32_t* n_dev, int m, int nc, int nb, float* logits,
+                      int64_t ld_logits, float* loss_acc, float* dfeat, int64_t ld_dfeat, float* dW, float* db,
+                      void* scratch, int64_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

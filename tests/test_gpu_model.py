@@ -153,3 +153,51 @@ def test_training_reduces_loss():
     for _ in range(15):
         last = t.train_step(data, label)["loss"]
     assert last < 0.7 * first, (first, last)
+
+
+@pytest.mark.parametrize("with_weight", [False, True])
+def test_fused_head_loss_matches_torch(with_weight):
+    """csrc/headloss.cu against torch.nn.Linear + the reference-semantics SegmentationLoss
+    (uresnet_sparse.py:25,36,44-82): loss, accuracy and every gradient."""
+    from uresnet_pytorch_b200.model import SegmentationLoss
+    from uresnet_pytorch_b200.sparseconvnet import functional as F
+    torch.manual_seed(5)
+    n, m, nc, nb = 3000, 16, 5, 4
+    dev = torch.device("cuda")
+    feat = torch.randn(n, m, device=dev, requires_grad=True)
+    lin = torch.nn.Linear(m, nc).to(dev)
+    label = torch.randint(0, nc, (n, 1), device=dev).float()
+    ids = torch.randint(0, nb - 1, (n,), device=dev)          # event nb-1 is absent on purpose
+    data = torch.zeros(n, 5, dtype=torch.float64, device=dev)
+    data[:, 3] = ids.double()
+    pw = (torch.rand(n, 1, device=dev) + 0.5) if with_weight else None
+
+    crit = SegmentationLoss()
+    crit.num_events = nb
+    loss_ref, acc_ref = crit([lin(feat)], [data], [label], [pw] if with_weight else None)
+    loss_ref.backward()
+    g_ref = (feat.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    feat.grad = None
+    lin.zero_grad()
+
+    loss, acc = F.head_loss(feat, lin, label, data[:, 3], nb, pix_w=pw)
+    (2.0 * loss).backward()   # exercises the upstream-gradient scaling
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    assert abs(acc.item() - float(acc_ref)) <= 1e-5
+    for a, b in zip((feat.grad, lin.weight.grad, lin.bias.grad), g_ref):
+        assert (a - 2.0 * b).abs().max().item() <= 2e-5 * (2.0 * b).abs().max().item() + 1e-9
+
+
+def test_fused_and_unfused_trainers_agree():
+    """Trainer(fused_loss=True) and the torch loss path give the same loss trajectory."""
+    from uresnet_pytorch_b200.model import Flags
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = Flags(DATA_DIM=3, SPATIAL_SIZE=64, URESNET_FILTERS=16, URESNET_NUM_STRIDES=3, NUM_CLASS=5)
+    data, label = event_blob(2, 64, seed=3)
+    out = []
+    for fused in (False, True):
+        tr = Trainer(flags, graph=False, events_per_step=2, seed=1, fused_loss=fused)
+        out.append([tr.train_step(data, label) for _ in range(3)])
+    for a, b in zip(*out):
+        assert abs(a["loss"] - b["loss"]) <= 2e-4 * abs(a["loss"])
+        assert abs(a["acc"] - b["acc"]) <= 1e-3

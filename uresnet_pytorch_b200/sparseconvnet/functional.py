@@ -339,3 +339,57 @@ class OutputGather(torch.autograd.Function):
                   md.seg_off.data_ptr(), md.seg.data_ptr(), ctx.rows, ctx.n_dev, C, d.data_ptr(), d.stride(0),
                   _stream())
         return d, None, None, None
+
+
+class HeadLoss(torch.autograd.Function):
+    """Fused Linear(m -> nc) + per-event mean cross-entropy + per-event accuracy (csrc/headloss.cu;
+    reference: uresnet_sparse.py:25,36,44-82).  Returns a tensor [2] = (total_loss, total_acc).  The
+    backward pass was already computed by the forward kernel for an upstream gradient of 1 on total_loss;
+    `backward` scales it by the incoming gradient of element 0."""
+
+    @staticmethod
+    def forward(ctx, feat, W, b, label, ids, nb, pix_w, rows, n_dev, unit_grad):
+        _check_cuda_f32(feat, W, b)
+        feat = _rowmajor(feat)
+        W = W.contiguous()
+        label = label.reshape(-1)
+        if label.dtype != torch.float32:
+            label = label.float()
+        if ids.dtype not in (torch.int32, torch.int64, torch.float32, torch.float64):
+            ids = ids.long()
+        codes = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
+        m, nc = feat.shape[1], W.shape[0]
+        L = _lib.load()
+        nbytes = L.b200scn_head_loss_scratch_bytes(rows, m, nc, nb)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+        out = torch.empty(2, dtype=torch.float32, device=feat.device)
+        need = feat.requires_grad or W.requires_grad
+        dfeat = torch.empty((rows, m), dtype=torch.float32, device=feat.device) if need else None
+        dW = torch.empty_like(W) if need else None
+        db = torch.empty(nc, dtype=torch.float32, device=feat.device) if need else None
+        if pix_w is not None:
+            pix_w = pix_w.reshape(-1).float()
+        _lib.call("b200scn_head_loss", feat.data_ptr(), feat.stride(0), W.data_ptr(), _lib.ptr(b), label.data_ptr(),
+                  label.stride(0), _lib.ptr(pix_w), pix_w.stride(0) if pix_w is not None else 0, ids.data_ptr(),
+                  codes[ids.dtype], ids.stride(0), rows, n_dev, m, nc, nb, None, 0, out.data_ptr(), _lib.ptr(dfeat),
+                  dfeat.stride(0) if dfeat is not None else 0, _lib.ptr(dW), _lib.ptr(db), scratch.data_ptr(), nbytes,
+                  _stream())
+        ctx.grads = (dfeat, dW, db)
+        ctx.unit_grad = unit_grad
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        dfeat, dW, db = ctx.grads
+        if not ctx.unit_grad:
+            g = gout[0]
+            dfeat, dW, db = dfeat * g, dW * g, db * g
+        return dfeat, dW, (db if ctx.has_bias else None), None, None, None, None, None, None, None
+
+
+def head_loss(feat, linear, label, ids, nb, pix_w=None, rows=None, n_dev=None, unit_grad=False):
+    """(total_loss, total_acc) of a torch.nn.Linear head + the reference's SegmentationLoss on `feat`."""
+    rows = feat.shape[0] if rows is None else rows
+    out = HeadLoss.apply(feat, linear.weight, linear.bias, label, ids, nb, pix_w, rows, n_dev, unit_grad)
+    return out[0], out[1].detach()

@@ -54,13 +54,14 @@ def shard_events(n_events, world, rank):
 
 class Trainer(object):
     def __init__(self, flags, lr=1e-3, graph=False, capacity=None, events_per_step=1, train=True, device=None,
-                 math_mode=None, seed=0, overlap_wgrad=True):
+                 math_mode=None, seed=0, overlap_wgrad=True, fused_loss=True):
         self.flags = flags
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.graph_mode = graph
         self.train = train
         self.events_per_step = events_per_step
         self.overlap_wgrad = overlap_wgrad
+        self.fused_loss = fused_loss  # head + loss + their backward in three kernels (csrc/headloss.cu)
         self.math_mode = scn.config.math_mode if math_mode is None else math_mode
         torch.manual_seed(seed)
         self.net = UResNet(flags).to(self.device)
@@ -105,8 +106,19 @@ class Trainer(object):
         """One forward (+ backward + optimiser step when training) on device tensors."""
         with scn.config.math(self.math_mode):
             with torch.set_grad_enabled(self.train):
-                logits = self.net(data)[0]
-                if valid is not None:
+                logits = None
+                if self.fused_loss:
+                    ncol = data.shape[1]
+                    feats = self.net.sparseModel((data[:, :ncol - 1], data[:, ncol - 1:].float()))
+                    loss, acc = scn_functional.head_loss(
+                        feats, self.net.linear, label, data[:, ncol - 2], max(self.events_per_step, 1),
+                        rows=feats.shape[0], n_dev=self.d_n.data_ptr() if valid is not None else None,
+                        unit_grad=True)
+                else:
+                    logits = self.net(data)[0]
+                if self.fused_loss:
+                    pass
+                elif valid is not None:
                     lab = torch.where(valid, label.reshape(-1), torch.zeros_like(label.reshape(-1)))
                     w = valid.float()
                     loss, acc = self._masked_loss(logits, data, lab, w)
