@@ -131,13 +131,14 @@ int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_s
                        int math_mode, void* stream);
 
 /* the same contraction driven by a grouped pair list (tensor-core math modes, channels % 16 == 0);
- * tile_end == NULL: scanned lists (stage 0 + 1), else fixed-stride lists (stage 2) */
+ * tile_end == NULL: scanned lists (stage 0 + 1), else fixed-stride lists (stage 2);
+ * n_out_expect: expected live row count when n_out_cap is a capacity (launch heuristics only; 0 = unknown) */
 /* Wp: optional fragment-ordered copy of W for this direction (b200scn_pack_weights with the same strides
  * and kflip), or NULL */
 int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
-                     int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end, const void* g_rec, int K,
-                     int64_t n_out_cap, const int32_t* n_out_dev, int Cin, int Cout, float* out, int64_t ldo,
-                     int accumulate, int math_mode, void* stream);
+                     int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
+                     const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int64_t n_out_expect, int Cin,
+                     int Cout, float* out, int64_t ldo, int accumulate, int math_mode, void* stream);
 
 /* Re-order weights into the mma fragment order b200scn_conv_gpl reads with coalesced 16-byte loads.
  * jobs_dev: device array of n_jobs records of int64[10] = {W ptr, out ptr, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0}

@@ -684,7 +684,7 @@ int launch_small(GplParams p, int passes, cudaStream_t st) {
     if (small_warps < 1 || small_warps > 16) small_warps = 16;
   }
   int warps = small_warps;
-  while (warps > 4 && warps * acc_bytes(R, MT) > (size_t)112 * 1024) warps >>= 1;  // two CTAs per SM
+  while (warps > 4 && warps * acc_bytes(R, MT) > (size_t)200 * 1024) warps >>= 1;
   const size_t smem = warps * acc_bytes(R, MT);
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(k_conv_gpl_small<MT, X3, R, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -847,8 +847,9 @@ extern "C" int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t
 
 extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
                                 int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
-                                const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int Cin,
-                                int Cout, float* out, int64_t ldo, int accumulate, int math_mode, void* stream) {
+                                const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev,
+                                int64_t n_out_expect, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
+                                int math_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16, "conv_gpl: channels must be multiples of 16");
   B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "conv_gpl: tensor-core math modes only");
@@ -883,7 +884,9 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
     }
   }
   // small inputs: narrow passes unless the tiles alone already cover the SMs twice
-  const int64_t tiles = cdiv(n_out_cap, tile_rows);
+  // (n_out_expect: how many rows the level really has when n_out_cap is only a buffer capacity)
+  const int64_t n_live = (n_out_expect > 0 && n_out_expect < n_out_cap) ? n_out_expect : n_out_cap;
+  const int64_t tiles = cdiv(n_live, tile_rows);
   const int MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
   if (MT == 1)
     return x3 ? launch_small_r<1, true>(p, cot, tile_rows, st) : launch_small_r<1, false>(p, cot, tile_rows, st);

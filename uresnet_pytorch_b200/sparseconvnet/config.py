@@ -30,6 +30,7 @@ pack_weights = not os.environ.get("B200SCN_NO_PACK")
 # static regime: tile rows per spatial size.  A level's capacity says nothing about how many rows it really
 # has, so the trainer calibrates this once on a real event (Trainer._calibrate_tiles)
 gpl_tile_rows_by_size = {}
+gpl_rows_by_size = {}  # the calibrated row counts themselves (launch heuristics)
 
 # static regime: levels below this capacity build their pair lists in one pass into fixed-stride slots
 gpl_fixed_stride_max_rows = 128 * 8 * 148

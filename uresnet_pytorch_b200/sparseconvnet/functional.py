@@ -139,7 +139,7 @@ def _conv_gpl(x, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
     Wp = packed_weights(W3, Cin, Cout, w_si, w_so, kflip) if config.pack_weights else None
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
               kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
-              n_out, n_out_dev,
+              n_out, n_out_dev, gpl.get("rows_hint", 0),
               Cin, Cout, out.data_ptr(), out.stride(0), 0, math, _stream())
     return out
 

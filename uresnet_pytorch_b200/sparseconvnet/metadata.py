@@ -184,7 +184,8 @@ class Metadata(object):
             g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)
             _lib.call("b200scn_gpl_build", 2, *tab, _lib.ptr(tile_off), _lib.ptr(tile_end), None, _lib.ptr(g_rec), cap,
                       None, 0, _stream())
-            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile)
+            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile,
+                        rows_hint=config.gpl_rows_by_size.get(size_key, 0))
         total = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -165,12 +165,15 @@ class Trainer(object):
         size = (int(self.flags.SPATIAL_SIZE),) * D
         lv = md.set_input(self.d_data[:n, :D + 1], size)
         hints = {size: L.b200scn_gpl_tile_rows(max(lv.n, 1))}
+        rows = {size: lv.n}
         for _ in range(int(self.flags.URESNET_NUM_STRIDES) - 1):
             out = tuple((v - 2) // 2 + 1 for v in size)
             md.down_rules(size, out, 2)
             hints[out] = L.b200scn_gpl_tile_rows(max(md.level(out).n, 1))
+            rows[out] = md.level(out).n
             size = out
         scn.config.gpl_tile_rows_by_size = hints
+        scn.config.gpl_rows_by_size = rows
 
     def _capture(self):
         """Warm up on a side stream, then capture the whole step into one CUDA graph."""
