@@ -3,6 +3,8 @@
 MATH_TF32X3 (3-term operand split) must be fp32-equivalent: same tolerances as the FFMA
 kernels.  MATH_TF32 (single pass, 10-bit mantissa operands) is the reduced-precision mode:
 max|d| <= 5e-3 * scale on outputs, rel-L2 <= 1e-2 on gradients."""
+import os
+
 import pytest
 import torch
 
@@ -164,3 +166,46 @@ def test_gpl_and_pairs_kernels_agree(mode):
         finally:
             scn.config.use_gpl = True
     assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (64, 32)])
+def test_large_input_gpl_kernel(mode, cin, cout):
+    """k_conv_gpl (one warp per 128-row tile, weights resident in shared memory -- the kernel bench.py's
+    roofline times) against the neighbour-table kernel.  Runs in a subprocess because the row threshold
+    that selects it is read once per process (B200SCN_GPL_LARGE_MIN_ROWS)."""
+    import subprocess
+    import sys
+    code = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from helpers import event_blob
+from uresnet_pytorch_b200 import sparseconvnet as scn, _lib
+from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+scn.config.gpl_tile_rows = 128
+data, _ = event_blob(6, 96, seed=21)
+coords = torch.from_numpy(data[:, :4]).cuda()
+md = Metadata(3); size = (96, 96, 96)
+lv = md.set_input(coords, size)
+nbr = md.subm_table(size, 3); gpl = md.subm_gpl(size, 3)
+assert gpl["tile_rows"] == 128 and gpl["tile_end"] is None
+n, K, Cin, Cout, mode = lv.n, 27, %d, %d, %d
+torch.manual_seed(1)
+x = torch.randn(n, Cin, device="cuda"); W = torch.randn(K, Cin, Cout, device="cuda") * 0.1
+st = torch.cuda.current_stream().cuda_stream
+for (si, so, flip, ci, co) in ((Cout, 1, 0, Cin, Cout), (1, Cout, 1, Cout, Cin)):
+    xin = x if ci == Cin else torch.randn(n, ci, device="cuda")
+    a = torch.empty(n, co, device="cuda"); b = torch.empty(n, co, device="cuda")
+    _lib.call("b200scn_conv_gpl", xin.data_ptr(), ci, W.data_ptr(), None, Cin * Cout, si, so, flip, 128,
+              gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, ci, co, a.data_ptr(), co, 0, mode, st)
+    _lib.call("b200scn_conv_table", xin.data_ptr(), ci, W.data_ptr(), Cin * Cout, si, so, flip, nbr.data_ptr(),
+              nbr.stride(0), K, n, None, ci, co, b.data_ptr(), co, 0, 0, st)
+    torch.cuda.synchronize()
+    tol = 3e-5 if mode == 1 else 5e-3
+    err = (a - b).abs().max().item() / b.abs().max().item()
+    assert err <= tol, err
+print("ok", n)
+""" % (os.path.dirname(os.path.abspath(__file__)), cin, cout, mode)
+    env = dict(os.environ, B200SCN_GPL_LARGE_MIN_ROWS="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -39,6 +39,7 @@ namespace {
 
 constexpr int kMaxSmem = 220 * 1024;
 constexpr int kLargeWarps = 20;
+constexpr int kRecRing = 8;  // per-warp shared-memory ring of group records (128 B each)
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // D(16 pairs x 8 co) += A(16 pairs x 8 ci) * B(8 ci x 8 co)
@@ -176,8 +177,8 @@ __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
 template <int Q, int MT, bool WSMEM, bool X3, int R>
 __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(const GplParams p) {
   constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
-  constexpr int DEPTH = Q == 1 ? 2 : 1;  // feature rows are fetched DEPTH groups ahead, records 2*DEPTH
-  constexpr int RING = 2 * DEPTH;
+  constexpr int DEPTH = Q <= 2 ? 3 : 2;  // register slots for gathered feature rows
+  constexpr int LEAD = DEPTH - 1;        // groups between a row request and its use
   // WREG: the B fragments of the current offset live in registers and are reloaded (raw fp32 from shared
   // memory, low parts recomputed) only when the offset changes -- the L1/shared data pipe is this
   // kernel's bottleneck (profiles/README.md), and the weights were a third of its shared-memory traffic
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t s_acc = s_base + acc_base + warp * kAccBytes + t * 8;  // + row * CT * 4 + chunk * 32
   const uint32_t s_whi = s_base + lane * 16, s_wlo = s_whi + w_elems * 4;
+  const uint32_t s_ring = s_base + acc_base + warps * kAccBytes + warp * (kRecRing * 128);
 
   if (WSMEM) {
     // fragment order: [(k, kstep s, mt)][lane][4] = {b0, b1 of n-tile 2mt, b0, b1 of n-tile 2mt+1}
@@ -253,7 +255,6 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   }
   const char* const in_l = reinterpret_cast<const char*>(p.in) + 16 * t;
   const uint32_t ldb = (uint32_t)p.ldi * 4u;  // row stride in bytes
-  const int4* const rec_l = p.g_rec + g;
   for (int64_t wt = wt_begin; wt < wt_end; wt += wt_stride) {
     const int base = (int)(wt * R);
     __syncwarp();
@@ -268,22 +269,27 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
     }
     __syncwarp();
 
-    // Software pipeline over a ring of RING record slots and DEPTH row slots; the loop body is unrolled
-    // RING times so that every slot index is static and no value is ever copied between slots (a copy
-    // of a just-issued load stalls the warp until the load returns).  Records and rows past the end of
-    // the range are clamped to the last group: redundant but unconditional loads, never consumed.
-    int Rx[RING], Ry[RING], Rz[RING];
+    // Software pipeline.  Group records stream through a per-warp shared-memory ring filled by cp.async
+    // kRecRing - 1 groups ahead (an async copy has no destination register, so ptxas cannot sink it next
+    // to its use the way it does with plain loads -- profiles/README.md); the feature rows of group
+    // i + LEAD are requested at the START of group i's body into one of DEPTH register slots.  The body is
+    // unrolled DEPTH times so every slot index is static.  Records and rows past the end of the range
+    // are clamped to the last group: redundant but unconditional, never consumed.
     float4 G[DEPTH][2][Q];
+    int Rz[DEPTH];
     const int g_last = max(ge - 1, gb);
-    auto fetch_rec = [&](int grp, int u) {
-      const int4* r = rec_l + (int64_t)min(grp, g_last) * 8;
-      Rx[u] = ldg_nc32(r);
-      Ry[u] = ldg_nc32(reinterpret_cast<const int*>(r) + 1);
-      Rz[u] = ldg_nc32(reinterpret_cast<const int*>(r) + 2);
+    const uint32_t ring_cp = s_ring + lane * 4, ring_rd = s_ring + g * 16;
+    auto fetch_rec = [&](int grp) {  // lane l copies word l of the 128-byte record
+      const int32_t* src = reinterpret_cast<const int32_t*>(p.g_rec + (int64_t)min(grp, g_last) * 8) + lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_cp + (uint32_t)(grp & (kRecRing - 1)) * 128u),
+                   "l"(src) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto fetch_rows = [&](int u, int d) {
-      const float4* s0 = reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)Rx[u] * ldb);
-      const float4* s1 = reinterpret_cast<const float4*>(in_l + (uint64_t)(uint32_t)Ry[u] * ldb);
+    auto fetch_rows = [&](int grp, int d) {  // record of `grp` must have landed in the ring
+      const float4 r = lds128(ring_rd + (uint32_t)(grp & (kRecRing - 1)) * 128u);
+      Rz[d] = __float_as_int(r.z);
+      const float4* s0 = reinterpret_cast<const float4*>(in_l + (uint64_t)__float_as_uint(r.x) * ldb);
+      const float4* s1 = reinterpret_cast<const float4*>(in_l + (uint64_t)__float_as_uint(r.y) * ldb);
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         G[d][0][q] = __ldg(s0 + 4 * q);
@@ -291,21 +297,30 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       }
     };
     if (gb < ge) {
+      __syncwarp();  // the previous tile's last ring reads are done
 #pragma unroll
-      for (int u = 0; u < RING; ++u) fetch_rec(gb + u, u);
+      for (int u = 0; u < kRecRing - 1; ++u) fetch_rec(gb + u);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - LEAD) : "memory");
+      __syncwarp();
 #pragma unroll
-      for (int d = 0; d < DEPTH; ++d) fetch_rows(d, d);
+      for (int d = 0; d < LEAD; ++d) fetch_rows(gb + d, d);
     }
 
     uint32_t wbh[WREG ? KS : 1][WREG ? MT : 1][4], wbl[WREG ? KS : 1][WREG ? MT : 1][4];
     int wcur = -1;
-    for (int g0 = gb; g0 < ge; g0 += RING) {
+    for (int g0 = gb; g0 < ge; g0 += DEPTH) {
 #pragma unroll
-      for (int u = 0; u < RING; ++u) {
+      for (int u = 0; u < DEPTH; ++u) {
         const int grp = g0 + u;
         if (grp >= ge) break;
-        const int d = u % DEPTH;
-        const uint32_t mz = (uint32_t)Rz[u];
+        const int d = u;
+        // (g0 - gb) is a multiple of DEPTH, so group `grp` sits in row slot u and group grp + LEAD in
+        // slot (u + LEAD) % DEPTH -- the slot released by group grp - 1
+        fetch_rec(grp + kRecRing - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - LEAD) : "memory");
+        __syncwarp();
+        fetch_rows(grp + LEAD, (u + LEAD) % DEPTH);
+        const uint32_t mz = (uint32_t)Rz[d];
         const int kk = (mz >> 16) & 0xff;
         const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
         const int x0 = (MT & 1) ? ((o0 >> 1) & 1) : (o0 & 3), x1 = (MT & 1) ? ((o1 >> 1) & 1) : (o1 & 3);
@@ -398,9 +413,6 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
             }
           }
         }
-        // refill the two slots this group has just released
-        fetch_rows((u + DEPTH) % RING, d);
-        fetch_rec(grp + RING, u);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           sts64(a0 + ((j ^ x0) << 5), dacc[j][0], dacc[j][1]);
@@ -652,7 +664,8 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   }
   const size_t fixed = w_smem_bytes(p.K, 16 * Q, MT, X3);
   int warps = large_warps();
-  while (warps > 1 && fixed + warps * acc_bytes(128, MT) > (size_t)kMaxSmem) --warps;
+  const size_t per_warp = acc_bytes(128, MT) + kRecRing * 128;
+  while (warps > 1 && fixed + warps * per_warp > (size_t)kMaxSmem) --warps;
   p.warps = warps;
   p.split = 0;
   const int64_t tiles = cdiv(p.n_cap, 128);
@@ -661,7 +674,7 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  k_conv_gpl<Q, MT, true, X3, 128><<<grid, warps * 32, fixed + warps * acc_bytes(128, MT), st>>>(p);
+  k_conv_gpl<Q, MT, true, X3, 128><<<grid, warps * 32, fixed + warps * per_warp, st>>>(p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
@@ -869,11 +882,16 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
 
   // large inputs (enough 128-row tiles to give every SM a CTA of one-tile warps) with scanned lists and
   // a weight slice that fits in shared memory next to >= 12 accumulators: k_conv_gpl
-  const bool large = tile_rows == 128 && tile_end == nullptr && Cin <= 64 && n_out_cap >= (int64_t)128 * 8 * sm_count();
+  static int64_t large_min = -1;  // B200SCN_GPL_LARGE_MIN_ROWS overrides the row threshold (tests)
+  if (large_min < 0) {
+    const char* e = getenv("B200SCN_GPL_LARGE_MIN_ROWS");
+    large_min = e ? atoll(e) : (int64_t)128 * 8 * sm_count();
+  }
+  const bool large = tile_rows == 128 && tile_end == nullptr && Cin <= 64 && n_out_cap >= large_min;
   if (large) {
     int MT = 0;
     for (int mt = 2; mt >= 1; --mt)
-      if (cot % mt == 0 && w_smem_bytes(K, Cin, mt, x3) + 12 * acc_bytes(128, mt) <= (size_t)kMaxSmem) { MT = mt; break; }
+      if (cot % mt == 0 && w_smem_bytes(K, Cin, mt, x3) + 12 * (acc_bytes(128, mt) + kRecRing * 128) <= (size_t)kMaxSmem) { MT = mt; break; }
     if (MT) {
       switch (p.Q) {
         case 1: return launch_large_q<1>(p, MT, cot / MT, x3, st);
