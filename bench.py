@@ -29,8 +29,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+METRIC = "sparse U-ResNet train voxels/sec at 512^3"
 CONFIG = dict(ss=512, uns=5, uf=16, nc=5, dim=3)
 WORKLOAD = "uresnet_sparse 3D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[1]), Adam, fp32"
+# other BASELINE.json configs, selectable with --config for parity / scaling runs (never the default line)
+EXTRA_CONFIGS = {
+    "c3": (dict(ss=512, uns=5, uf=16, nc=5, dim=2), 16,
+           "uresnet_sparse 2D train ss=512 uns=5 uf=16 nc=5 bs=%d per GPU (BASELINE configs[2]), Adam, fp32"),
+    "c5": (dict(ss=768, uns=6, uf=32, nc=5, dim=3), 8,
+           "uresnet_sparse 3D train ss=768 uns=6 uf=32 nc=5 bs=%d per GPU (BASELINE configs[4]), Adam, fp32"),
+}
 
 
 def parse():
@@ -41,6 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=1)
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic steps cycled through")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = BASELINE configs[1] (the metric's config, default); c3 / c5 = configs[2] / configs[4]")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep wgrad kernels on the main stream")
@@ -49,7 +59,16 @@ def parse():
     ap.add_argument("--math", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="fp32: FFMA kernels; tf32x3: tensor-core 3-term split, fp32-equivalent (parity-tested at the "
                          "fp32 tolerances); tf32: single-pass tensor core (reduced precision)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config != "c2":
+        global WORKLOAD, METRIC
+        cfg, bs, WORKLOAD = EXTRA_CONFIGS[args.config]
+        CONFIG.update(cfg)
+        METRIC = "sparse U-ResNet train voxels/sec at %d^%d" % (cfg["ss"], cfg["dim"])
+        if args.events_per_gpu == 1:
+            args.events_per_gpu = bs
+        args.no_roofline = True
+    return args
 
 
 def peaks():
@@ -156,7 +175,7 @@ def run_reference(args):
     total_t, total_v = sum(times), sum(vox)
     value = total_v / total_t
     line = {
-        "impl": "reference", "metric": "sparse U-ResNet train voxels/sec at 512^3", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -360,7 +379,7 @@ def run_b200(args):
                          "(bs=%d, 512^3); %.2f s/step" % (args.events_per_gpu, sum(times) / len(times))}
 
     line = {
-        "metric": "sparse U-ResNet train voxels/sec at 512^3", "value": vox_all / dev_s, "unit": "voxels/s",
+        "metric": METRIC, "value": vox_all / dev_s, "unit": "voxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "f32 (storage and accumulation fp32; products via 3-term tf32 split on mma.sync, fp32-equivalent: tests/test_gpu_mma.py)", "tf32": "tf32 (reduced precision)"}[args.math], "data": "synthetic",

@@ -20,20 +20,25 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--math", default="tf32x3")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--no-overlap", action="store_true")
+ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"])
 a = ap.parse_args()
 mode = {"fp32": scn.MATH_FP32, "tf32x3": scn.MATH_TF32X3, "tf32": scn.MATH_TF32}[a.math]
+events = 1
+if a.config != "c2":
+    cfg, events, _ = bench.EXTRA_CONFIGS[a.config]
+    bench.CONFIG.update(cfg)
 C = bench.CONFIG
 flags = Flags(DATA_DIM=C["dim"], SPATIAL_SIZE=C["ss"], URESNET_FILTERS=C["uf"], URESNET_NUM_STRIDES=C["uns"],
               NUM_CLASS=C["nc"])
 
 
 class A(object):
-    events_per_gpu, pool = 1, 4
+    events_per_gpu, pool = events, 4
 
 
 pool = bench.make_pool(A, 0)
 cap = ((max(len(d) for d, _ in pool) * 9 // 8 + 4095) // 4096) * 4096 * int(os.environ.get("B200SCN_BENCH_CAP_MULT", "1"))
-tr = Trainer(flags, graph=True, capacity=cap, events_per_step=1, math_mode=mode, overlap_wgrad=not a.no_overlap)
+tr = Trainer(flags, graph=True, capacity=cap, events_per_step=events, math_mode=mode, overlap_wgrad=not a.no_overlap)
 for i in range(4):
     tr.train_step(*pool[i % 4])
 torch.cuda.synchronize()

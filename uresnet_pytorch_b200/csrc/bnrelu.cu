@@ -142,8 +142,21 @@ __global__ void k_bn_apply_train(const float* __restrict__ x, int64_t ldx, int64
   if (blockIdx.x != 0 && (int64_t)blockIdx.x * RL >= n) return;
   const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
+    // fold this lane's share of the partial blocks: four blocks' loads in flight per step (the merge is a
+    // serial chain, the L2 round trips need not be), merged in block order
     float N = 0.f, M = 0.f, S = 0.f;
-    for (int b = rl; b < nblk; b += RL) {
+    int b = rl;
+    for (; b + 3 * RL < nblk; b += 4 * RL) {
+      float pn[4], pm[4], ps[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = part + (int64_t)(b + u * RL) * 3 * C;
+        pn[u] = __ldcg(p + c); pm[u] = __ldcg(p + C + c); ps[u] = __ldcg(p + 2 * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) chan_merge(N, M, S, pn[u], pm[u], ps[u]);
+    }
+    for (; b < nblk; b += RL) {
       const float* p = part + (int64_t)b * 3 * C;
       chan_merge(N, M, S, __ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c));
     }
@@ -246,7 +259,18 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const f
   const int nblk = live_blocks(n, grid_stats, rows_per_blk);
   {
     float a1 = 0.f, a2 = 0.f;
-    for (int bk = rl; bk < nblk; bk += RL) {
+    int bk = rl;
+    for (; bk + 3 * RL < nblk; bk += 4 * RL) {  // four blocks' loads in flight, summed in block order
+      float v1[4], v2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = part + (int64_t)(bk + u * RL) * 2 * C;
+        v1[u] = __ldcg(p + c); v2[u] = __ldcg(p + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a1 += v1[u]; a2 += v2[u]; }
+    }
+    for (; bk < nblk; bk += RL) {
       const float* p = part + (int64_t)bk * 2 * C;
       a1 += __ldcg(p + c);
       a2 += __ldcg(p + C + c);

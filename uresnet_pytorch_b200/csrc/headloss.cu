@@ -32,11 +32,23 @@ __device__ __forceinline__ int read_id(const void* ids, int dtype, int64_t ld, i
 
 __global__ void k_hl_count(const void* __restrict__ ids, int id_dtype, int64_t ld_ids, int64_t n_cap,
                            const int32_t* __restrict__ n_dev, int nb, int32_t* __restrict__ cnt) {
+  // per-CTA histogram in shared memory first (events are few and a whole event hits ONE counter), then one
+  // global atomic per (CTA, event present in it)
+  constexpr int kHist = 1024;
+  __shared__ int hist[kHist];
   const int n = live_rows(n_dev, n_cap);
+  const bool use_hist = nb <= kHist;
+  if (use_hist)
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) hist[e] = 0;
+  __syncthreads();
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     const int b = read_id(ids, id_dtype, ld_ids, r);
-    if (b >= 0 && b < nb) atomicAdd(cnt + b, 1);
+    if (b >= 0 && b < nb) atomicAdd(use_hist ? hist + b : cnt + b, 1);
   }
+  __syncthreads();
+  if (use_hist)
+    for (int e = threadIdx.x; e < nb; e += blockDim.x)
+      if (hist[e] != 0) atomicAdd(cnt + e, hist[e]);
 }
 
 struct HlParams {
