@@ -108,14 +108,16 @@ int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_de
  * stage 0 -> tile_off[tiles + 1] (scanned group offsets), total_dev[1];
  * stage 1 -> g_rec[128 B * cap_groups] at those offsets (tile t = groups tile_off[t] .. tile_off[t+1]);
  * stage 2 -> single pass, fixed-stride slots: tile_off[tiles] = begin, tile_end[tiles] = end of every tile,
- *            cap_groups >= b200scn_gpl_max_groups(); no scan and no read-back (CUDA-graph regime). */
+ *            cap_groups >= b200scn_gpl_max_groups(); no scan and no read-back (CUDA-graph regime).
+ * koff (optional, stages 1 and 2): int32[tiles * (K + 1)], first group of every offset inside each tile
+ * (entry K = end of the tile) -- the index b200scn_wgrad_gpl walks. */
 int b200scn_gpl_tile_rows(int64_t n); /* recommended tile_rows for a level of n rows */
 int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows);
 int64_t b200scn_gpl_scratch_bytes(int64_t n_cap);
 int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs, int K,
                       int64_t n_cap, const int32_t* n_dev, int tile_rows, int32_t* tile_off, int32_t* tile_end,
-                      int32_t* total_dev, void* g_rec, int64_t cap_groups, void* scratch, int64_t scratch_bytes,
-                      void* stream);
+                      int32_t* total_dev, void* g_rec, int64_t cap_groups, int32_t* koff, void* scratch,
+                      int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (ii) gather-GEMM(-scatter) convolutions -- SubmanifoldConvolution / Convolution /
@@ -163,6 +165,15 @@ int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, int64_t ldb
                         int64_t ld, int K, int gather_b, int64_t n_cap, const int32_t* n_dev, int Ca, int Cb,
                         float* dW, int accumulate, int math_mode, void* scratch, int64_t scratch_bytes,
                         void* stream);
+
+/* Weight gradients over a grouped pair list (tensor-core math modes, channels % 16 == 0): the list must be the
+ * one the layer's FORWARD uses (its in rows index A = layer input, its out rows index B = output gradient).
+ * subm != 0: offset K/2 is the dense centre of a submanifold convolution (gets extra CTAs).  Deterministic. */
+int64_t b200scn_wgrad_gpl_scratch_bytes(int K, int Ca, int Cb);
+int b200scn_wgrad_gpl(const float* A, int64_t lda, const float* B, int64_t ldb, int tile_rows, const void* g_rec,
+                      const int32_t* koff, int K, int subm, int64_t n_cap, const int32_t* n_dev, int64_t n_expect,
+                      int Ca, int Cb, float* dW, int accumulate, int math_mode, void* scratch, int64_t scratch_bytes,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (iii) fused BatchNorm + (leaky) ReLU -- scn.BatchNormReLU (uresnet_sparse.py:23) and

@@ -56,7 +56,8 @@ template <bool FILL, int R>
 __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const int32_t* __restrict__ parent,
                             const uint8_t* __restrict__ kofs, int K, int64_t n_cap, const int32_t* __restrict__ n_dev,
                             int32_t* __restrict__ tile_cnt, const int32_t* __restrict__ tile_off,
-                            int32_t* __restrict__ tile_beg_out, int4* __restrict__ g_rec, int64_t cap_groups) {
+                            int32_t* __restrict__ tile_beg_out, int4* __restrict__ g_rec, int64_t cap_groups,
+                            int32_t* __restrict__ koff) {
   constexpr int NR = R / 32;  // rows per lane
   const int n = live_rows(n_dev, n_cap);
   const int lane = threadIdx.x & 31;
@@ -82,6 +83,7 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
     for (int k = 0; k < K; ++k) {
       int e[NR], pre[NR];
       int cnt = 0;
+      if (FILL && koff != nullptr && lane == 0) koff[tile * (K + 1) + k] = (int32_t)grp;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int r = base + 32 * i + lane;
@@ -121,6 +123,7 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
       grp += ng;
       count += ng;
     }
+    if (FILL && koff != nullptr && lane == 0) koff[tile * (K + 1) + K] = (int32_t)grp;
     if (!FILL && lane == 0) tile_cnt[tile] = count;
     if (fixed && lane == 0) {
       tile_beg_out[tile] = (int32_t)grp0;
@@ -784,19 +787,20 @@ extern "C" int64_t b200scn_gpl_scratch_bytes(int64_t n_cap) {
 template <bool FILL>
 static void launch_build(int tile_rows, int grid, int threads, cudaStream_t st, const int32_t* table, int64_t ld,
                          const int32_t* parent, const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev,
-                         int32_t* tile_cnt, const int32_t* tile_off, int32_t* tile_beg_out, int4* rec, int64_t cap) {
+                         int32_t* tile_cnt, const int32_t* tile_off, int32_t* tile_beg_out, int4* rec, int64_t cap,
+                         int32_t* koff) {
   switch (tile_rows) {
     case 32:
       k_gpl_build<FILL, 32><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                      tile_beg_out, rec, cap);
+                                                      tile_beg_out, rec, cap, koff);
       break;
     case 64:
       k_gpl_build<FILL, 64><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                      tile_beg_out, rec, cap);
+                                                      tile_beg_out, rec, cap, koff);
       break;
     default:
       k_gpl_build<FILL, 128><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                       tile_beg_out, rec, cap);
+                                                       tile_beg_out, rec, cap, koff);
   }
 }
 
@@ -807,7 +811,8 @@ static void launch_build(int tile_rows, int grid, int threads, cudaStream_t st, 
 extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent,
                                  const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int tile_rows,
                                  int32_t* tile_off, int32_t* tile_end, int32_t* total_dev, void* g_rec,
-                                 int64_t cap_groups, void* scratch, int64_t scratch_bytes, void* stream) {
+                                 int64_t cap_groups, int32_t* koff, void* scratch, int64_t scratch_bytes,
+                                 void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= 64, "gpl_build: K must be 1..64");
   B200_CHECK_ARG(tile_rows == 32 || tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 32, 64 or 128");
@@ -825,21 +830,21 @@ extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, co
     B200_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(tiles + 8) * 4, st));
     if (n_cap > 0)
       launch_build<false>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
-                          nullptr, nullptr, nullptr, 0);
+                          nullptr, nullptr, nullptr, 0, nullptr);
     // exclusive scan over all `tiles` counts (tiles beyond the live ones hold 0)
     if (int rc = scan_i32_public(tile_cnt, tile_off, tiles, nullptr, total_dev, tile_off, bsums, st)) return rc;
     count_launches(4);
   } else if (stage == 1) {
     if (n_cap > 0)
       launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
-                         tile_off, nullptr, rec, cap_groups);
+                         tile_off, nullptr, rec, cap_groups, koff);
     count_launches(1);
   } else {
     B200_CHECK_ARG(tile_end != nullptr, "gpl_build: stage 2 needs tile_end");
     B200_CHECK_ARG(cap_groups >= b200scn_gpl_max_groups(n_cap, K, tile_rows), "gpl_build: stage 2 needs worst-case capacity");
     if (n_cap > 0)
       launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_end,
-                         nullptr, tile_off, rec, cap_groups);
+                         nullptr, tile_off, rec, cap_groups, koff);
     count_launches(1);
   }
   B200_CHECK_LAUNCH("gpl_build");

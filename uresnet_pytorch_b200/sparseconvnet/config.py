@@ -24,6 +24,9 @@ gpl_min_rows = int(os.environ.get("B200SCN_GPL_MIN_ROWS", "0"))
 # rows per tile of the grouped pair lists (64 / 128); None = the library's recommendation for the level size
 gpl_tile_rows = int(os.environ["B200SCN_GPL_TILE_ROWS"]) if os.environ.get("B200SCN_GPL_TILE_ROWS") else None
 
+# True: weight gradients walk the forward pair list (csrc/wgrad_gpl.cu) instead of the neighbour table
+wgrad_gpl = not os.environ.get("B200SCN_NO_WGRAD_GPL")
+
 # True: convolutions over grouped pair lists read a fragment-ordered copy of the weights (functional.packed_weights)
 pack_weights = not os.environ.get("B200SCN_NO_PACK")
 

@@ -49,16 +49,26 @@ def join_side_streams():
     del _side_keepalive[:]
 
 
-def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
+def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=False):
+    """dW [K, Ca, Cb].  `gpl`: the layer's FORWARD pair list (its out rows index B) -- when given, and the
+    shapes allow, the weight gradient walks it (csrc/wgrad_gpl.cu) instead of re-compacting the table."""
     Ca, Cb = A.shape[1], B.shape[1]
     L = _lib.load()
-    nbytes = L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
+    use_gpl = (gpl is not None and gpl.get("koff") is not None and config.use_gpl and config.wgrad_gpl and math != 0
+               and Ca % 16 == 0 and Cb % 16 == 0 and A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0
+               and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
+    nbytes = L.b200scn_wgrad_gpl_scratch_bytes(K, Ca, Cb) if use_gpl else L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
 
     # every buffer is allocated on the main stream; only the kernels move to the side stream
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
     dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
 
     def run():
+        if use_gpl:
+            _lib.call("b200scn_wgrad_gpl", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), gpl["tile_rows"],
+                      gpl["g_rec"].data_ptr(), gpl["koff"].data_ptr(), K, int(subm), rows, n_dev,
+                      gpl.get("rows_hint", 0), Ca, Cb, dW.data_ptr(), 0, math, scratch.data_ptr(), nbytes, _stream())
+            return
         _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
                   table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0,
                   math, scratch.data_ptr(), nbytes, _stream())
@@ -71,7 +81,7 @@ def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math):
     side.wait_stream(main)
     with torch.cuda.stream(side):
         run()
-    _side_keepalive.append((scratch, A, B, table))
+    _side_keepalive.append((scratch, A, B, table, gpl))
     _side_dirty.add((A.device.type, A.device.index))
     return dW
 
@@ -167,6 +177,7 @@ class TableConv(torch.autograd.Function):
                       out.data_ptr(), out.stride(0), 0, math, _stream())
         ctx.save_for_backward(x, W3)
         ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math, gpl_bwd)
+        ctx.gpl_fwd = gpl_fwd
         return out
 
     @staticmethod
@@ -192,7 +203,7 @@ class TableConv(torch.autograd.Function):
                           parent.data_ptr(), kofs.data_ptr(), K, n_in, n_in_dev, Cout, Cin, dx.data_ptr(),
                           dx.stride(0), math, _stream())
         if ctx.needs_input_grad[1]:
-            dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math)
+            dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math, ctx.gpl_fwd, symmetric)
         return dx, dW, None, None, None, None, None, None, None, None, None, None
 
 
@@ -216,6 +227,7 @@ class ParentConv(torch.autograd.Function):
                       out.stride(0), math, _stream())
         ctx.save_for_backward(x, W3)
         ctx.misc = (parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math, gpl_bwd)
+        ctx.gpl_fwd = gpl_fwd
         return out
 
     @staticmethod
@@ -235,7 +247,11 @@ class ParentConv(torch.autograd.Function):
                       dx.stride(0), 0, math, _stream())
         if ctx.needs_input_grad[1]:
             # dW[k] = sum_j x[j]^T @ dout[child[k][j]]
-            dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math)
+            if ctx.gpl_fwd is not None and ctx.gpl_fwd.get("koff") is not None:
+                # the forward list runs over the FINE rows (in = parent row, out = fine row): rows = n_fine
+                dW = _wgrad(x, dout, child, K, 1, n_fine, n_fine_dev, W3.shape, math, ctx.gpl_fwd, False)
+            else:
+                dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math)
         return dx, dW, None, None, None, None, None, None, None, None, None
 
 

@@ -175,6 +175,7 @@ class Metadata(object):
         tiles = max((max(rows, 1) + tile - 1) // tile, 1)
         dev = self.device
         tile_off = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
+        koff = torch.empty(tiles * (K + 1), dtype=torch.int32, device=dev)  # per-(tile, offset) group index
         tab = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
                nd, tile)
         if self.static and rows < config.gpl_fixed_stride_max_rows:
@@ -183,22 +184,23 @@ class Metadata(object):
             tile_end = torch.empty(tiles, dtype=torch.int32, device=dev)
             g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)
             _lib.call("b200scn_gpl_build", 2, *tab, _lib.ptr(tile_off), _lib.ptr(tile_end), None, _lib.ptr(g_rec), cap,
-                      None, 0, _stream())
-            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile,
+                      _lib.ptr(koff), None, 0, _stream())
+            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile, koff=koff,
                         rows_hint=config.gpl_rows_by_size.get(size_key, 0))
         total = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.call("b200scn_gpl_build", 0, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), None, 0, _lib.ptr(scratch),
-                  nbytes, _stream())
+        _lib.call("b200scn_gpl_build", 0, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), None, 0, None,
+                  _lib.ptr(scratch), nbytes, _stream())
         if self.static:
             cap = L.b200scn_gpl_max_groups(max(rows, 1), K, tile)
         else:
             cap = max(int(total.item()), 1)
         g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)  # [cap][8] int4 records
         _lib.call("b200scn_gpl_build", 1, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), _lib.ptr(g_rec), cap,
-                  _lib.ptr(scratch), nbytes, _stream())
-        return dict(tile_off=tile_off, tile_end=None, g_rec=g_rec, K=K, tile_rows=tile)
+                  _lib.ptr(koff), _lib.ptr(scratch), nbytes, _stream())
+        return dict(tile_off=tile_off, tile_end=None, g_rec=g_rec, K=K, tile_rows=tile, koff=koff,
+                    rows_hint=config.gpl_rows_by_size.get(size_key, 0) if self.static else 0)
 
     def subm_gpl(self, spatial_size, filter_size):
         lv = self.level(spatial_size)
