@@ -910,7 +910,13 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   // (n_out_expect: how many rows the level really has when n_out_cap is only a buffer capacity)
   const int64_t n_live = (n_out_expect > 0 && n_out_expect < n_out_cap) ? n_out_expect : n_out_cap;
   const int64_t tiles = cdiv(n_live, tile_rows);
-  const int MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
+  static int force_mt = -1;  // B200SCN_GPL_SMALL_MT = 1 / 2 forces the pass width (A/B runs)
+  if (force_mt < 0) {
+    const char* e = getenv("B200SCN_GPL_SMALL_MT");
+    force_mt = e ? atoi(e) : 0;
+  }
+  int MT = (cot % 2 == 0 && tiles * (cot / 2) >= sm_count()) ? 2 : 1;
+  if (force_mt == 1 || (force_mt == 2 && cot % 2 == 0)) MT = force_mt;
   if (MT == 1)
     return x3 ? launch_small_r<1, true>(p, cot, tile_rows, st) : launch_small_r<1, false>(p, cot, tile_rows, st);
   return x3 ? launch_small_r<2, true>(p, cot / 2, tile_rows, st) : launch_small_r<2, false>(p, cot / 2, tile_rows, st);

@@ -258,10 +258,10 @@ WggPlan wgg_plan(int K, int Ca, int Cb, int64_t n_cap, int64_t n_expect, int til
   // other offset, so its tile range is shared by 1 + extra CTAs
   pl.centre = (subm && (K & 1)) ? K / 2 : -1;
   pl.extra = pl.centre >= 0 ? 4 : 0;
-  static int target = 0;  // B200SCN_WGG_CTAS: CTAs aimed at (default 4 x SMs)
+  static int target = 0;  // B200SCN_WGG_CTAS: CTAs aimed at (default: one per SM -- more CTAs mean more partial blocks to write and fold)
   if (target == 0) {
     const char* e = getenv("B200SCN_WGG_CTAS");
-    target = e ? atoi(e) : 4 * sm_count();
+    target = e ? atoi(e) : sm_count();
     if (target < 1) target = 1;
   }
   const int64_t n_live = (n_expect > 0 && n_expect < n_cap) ? n_expect : n_cap;
