@@ -256,6 +256,13 @@ int b200scn_head_loss(const float* feat, int64_t ldf, const float* W, const floa
                       int64_t ld_logits, float* loss_acc, float* dfeat, int64_t ld_dfeat, float* dW, float* db,
                       void* scratch, int64_t scratch_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (viii) optimiser: torch.optim.Adam (defaults; /root/reference/uresnet/trainval.py:21-30,159-167) over all
+ * parameters in one launch.  jobs_dev: n_jobs records of int64[5] = {param, grad, exp_avg, exp_avg_sq, numel};
+ * step_dev[1]: number of steps taken so far (incremented by the kernel); ticket_dev[1]: zero-initialised. */
+int b200scn_adam_step(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, int32_t* step_dev, uint32_t* ticket_dev,
+                      float lr, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

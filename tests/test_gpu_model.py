@@ -201,3 +201,31 @@ def test_fused_and_unfused_trainers_agree():
     for a, b in zip(*out):
         assert abs(a["loss"] - b["loss"]) <= 2e-4 * abs(a["loss"])
         assert abs(a["acc"] - b["acc"]) <= 1e-3
+
+
+def test_fused_adam_matches_torch_adam():
+    """csrc/optim.cu (one launch for all tensors, device-side step counter) against torch.optim.Adam."""
+    from uresnet_pytorch_b200.optim import FusedAdam
+    torch.manual_seed(11)
+    shapes = [(27, 16, 16), (16,), (8, 32, 48), (5, 16), (1,)]
+    pa = [torch.randn(s, device="cuda") for s in shapes]
+    pb = [p.clone() for p in pa]
+    ref = torch.optim.Adam(pa, lr=3e-3)
+    mine = FusedAdam(pb, lr=3e-3)
+    for step in range(6):
+        gs = [torch.randn_like(p) * (0.1 + step) for p in pa]
+        for p, q, g in zip(pa, pb, gs):
+            p.grad = g.clone()
+            q.grad = g.clone()
+        ref.step()
+        mine.step()
+    for p, q in zip(pa, pb):
+        assert (p - q).abs().max().item() <= 2e-6 * max(1.0, p.abs().max().item())
+    assert int(mine.step_dev.item()) == 6
+    # a parameter without a gradient is left untouched (the step counter is global, unlike torch's per-tensor one)
+    before = pb[1].clone()
+    for q in pb:
+        q.grad = torch.ones_like(q)
+    pb[1].grad = None
+    mine.step()
+    assert torch.equal(pb[1], before) and int(mine.step_dev.item()) == 7

@@ -80,6 +80,14 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
     int64_t grp = FILL ? (fixed ? tile * (int64_t)K * (R / 16) : (int64_t)tile_off[tile]) : 0;
     const int64_t grp0 = grp;
     int count = 0;
+    // table entries of offset k + 1 are requested while offset k is being listed (the per-offset work is a
+    // short dependent chain, the L2 round trip of the table column would otherwise dominate it)
+    int nxt[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = base + 32 * i + lane;
+      nxt[i] = (table != nullptr && parent == nullptr && r < n) ? __ldg(table + r) : -1;
+    }
     for (int k = 0; k < K; ++k) {
       int e[NR], pre[NR];
       int cnt = 0;
@@ -91,7 +99,8 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
         if (parent != nullptr) {
           e[i] = pk[i] == k ? pp[i] : -1;
         } else if (table != nullptr) {
-          if (r < n) e[i] = __ldg(table + (int64_t)k * ld + r);
+          e[i] = nxt[i];
+          nxt[i] = (k + 1 < K && r < n) ? __ldg(table + (int64_t)(k + 1) * ld + r) : -1;
         } else {
           if (r < n) e[i] = r;
         }

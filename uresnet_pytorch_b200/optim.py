@@ -1,0 +1,66 @@
+"""Multi-tensor Adam over the C-ABI (csrc/optim.cu): torch.optim.Adam's default update
+(/root/reference/uresnet/trainval.py:159-167 builds `torch.optim.Adam(net.parameters(), lr=...)`) for every
+parameter in ONE kernel launch.  The step counter lives on the device, so the launch can be captured in a
+CUDA graph; gradient pointers are re-read on every call (autograd allocates fresh gradient tensors), through
+a pinned staging buffer so that the refresh is a capturable async copy.  One step counter for all tensors
+(torch keeps one per tensor; they agree whenever every parameter receives a gradient every step, as here)."""
+import torch
+
+from . import _lib
+
+
+class FusedAdam(object):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("FusedAdam: no parameters")
+        dev = self.params[0].device
+        if any((not p.is_cuda) or p.dtype != torch.float32 or not p.is_contiguous() for p in self.params):
+            raise RuntimeError("FusedAdam: parameters must be contiguous float32 CUDA tensors (there is no CPU path)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        n = len(self.params)
+        self._host = torch.zeros((n, 5), dtype=torch.int64).pin_memory()
+        self._jobs = torch.zeros((n, 5), dtype=torch.int64, device=dev)
+        self._max = max(p.numel() for p in self.params)
+        for i, p in enumerate(self.params):
+            self._host[i, 0] = p.data_ptr()
+            self._host[i, 2] = self.exp_avg[i].data_ptr()
+            self._host[i, 3] = self.exp_avg_sq[i].data_ptr()
+            self._host[i, 4] = p.numel()
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def reset_state(self):
+        """Forget the moments and the step count (used after warm-up iterations before graph capture)."""
+        for t in self.exp_avg + self.exp_avg_sq:
+            t.zero_()
+        self.step_dev.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        live = [i for i, p in enumerate(self.params) if p.grad is not None]
+        if not live:
+            return
+        for i in live:
+            g = self.params[i].grad
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                self.params[i].grad = g = g.float().contiguous()
+            self._host[i, 1] = g.data_ptr()
+        if len(live) == len(self.params):
+            host, jobs, n = self._host, self._jobs, len(self.params)
+        else:  # parameters without a gradient are skipped, as torch.optim does
+            host = self._host[live].contiguous().pin_memory()
+            jobs, n = self._jobs[:len(live)], len(live)
+        jobs.copy_(host, non_blocking=True)
+        self._keep = host
+        _lib.call("b200scn_adam_step", jobs.data_ptr(), n, self._max, self.step_dev.data_ptr(), self.ticket.data_ptr(),
+                  self.lr, self.betas[0], self.betas[1], self.eps, torch.cuda.current_stream().cuda_stream)

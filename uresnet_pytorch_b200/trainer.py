@@ -76,7 +76,12 @@ class Trainer(object):
         self.n_params = sum(p.numel() for p in self.params)
         self.opt = None
         if train:
-            self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, fused=True)
+            # one launch for all ~190 parameter tensors (csrc/optim.cu); B200SCN_TORCH_ADAM=1 keeps torch's
+            if os.environ.get("B200SCN_TORCH_ADAM"):
+                self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, fused=True)
+            else:
+                from .optim import FusedAdam
+                self.opt = FusedAdam(self.params, lr=lr)
         self.ncol = flags.DATA_DIM + 2
         self._graph = None
         self._cap = 0
@@ -212,10 +217,13 @@ class Trainer(object):
         self.net.load_state_dict(state)
         scn_functional.repack_all()
         if self.train:
-            for st in self.opt.state.values():
-                for k, v in st.items():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            if hasattr(self.opt, "reset_state"):
+                self.opt.reset_state()
+            else:
+                for st in self.opt.state.values():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.zero_()
         del opt_state
         torch.cuda.synchronize(self.device)
 
