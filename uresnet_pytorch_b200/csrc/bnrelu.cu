@@ -303,6 +303,60 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const f
   }
 }
 
+// Large inputs: hundreds of partial blocks.  Folding them inside every apply CTA is O(CTAs x blocks) L2
+// traffic (270 MB per BatchNorm layer at 300 k rows x 32 channels -- 20x the feature matrix); one CTA folds
+// them once instead and the apply kernels read a single merged block.
+__global__ void k_bn_merge_stats(const float* __restrict__ part, int64_t n_cap, const int32_t* __restrict__ n_dev, int C,
+                                 int RL, int rows_per_blk, int grid_stats, float* __restrict__ merged) {
+  extern __shared__ float sm[];  // [3][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int nblk = live_blocks(n, grid_stats, rows_per_blk);
+  float N = 0.f, M = 0.f, S = 0.f;
+  int b = rl;
+  for (; b + 3 * RL < nblk; b += 4 * RL) {
+    float pn[4], pm[4], ps[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* p = part + (int64_t)(b + u * RL) * 3 * C;
+      pn[u] = __ldcg(p + c); pm[u] = __ldcg(p + C + c); ps[u] = __ldcg(p + 2 * C + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) chan_merge(N, M, S, pn[u], pm[u], ps[u]);
+  }
+  for (; b < nblk; b += RL) {
+    const float* p = part + (int64_t)b * 3 * C;
+    chan_merge(N, M, S, __ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c));
+  }
+  sm[t] = N; sm[T + t] = M; sm[2 * T + t] = S;
+  chan_tree_merge(sm, T, C, RL, c, rl);
+  if (rl == 0) { merged[c] = sm[c]; merged[C + c] = sm[T + c]; merged[2 * C + c] = sm[2 * T + c]; }
+}
+
+__global__ void k_bn_merge_sums(const float* __restrict__ part, int64_t n_cap, const int32_t* __restrict__ n_dev, int C,
+                                int RL, int rows_per_blk, int grid_stats, float* __restrict__ merged) {
+  extern __shared__ float sm[];  // [2][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int nblk = live_blocks(n, grid_stats, rows_per_blk);
+  float a1 = 0.f, a2 = 0.f;
+  for (int bk = rl; bk < nblk; bk += RL) {
+    const float* p = part + (int64_t)bk * 2 * C;
+    a1 += __ldcg(p + c);
+    a2 += __ldcg(p + C + c);
+  }
+  sm[t] = a1; sm[T + t] = a2;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) { a1 += sm[j * C + c]; a2 += sm[T + j * C + c]; }
+    merged[c] = a1; merged[C + c] = a2;
+  }
+}
+
+constexpr int kMergeAbove = 64;  // partial blocks beyond which the merge runs as its own launch
+
 int apply_grid(int64_t n_cap, int RL) {
   int64_t g = cdiv(n_cap, (int64_t)RL * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -318,7 +372,7 @@ using namespace b200scn;
 
 extern "C" int64_t b200scn_bn_scratch_bytes(int64_t n_cap, int C) {
   Layout L = make_layout(n_cap < 1 ? 1 : n_cap, C < 1 ? 1 : C);
-  return 256 + (int64_t)L.blocks * 3 * C * 4;
+  return 256 + (int64_t)(L.blocks + 1) * 3 * C * 4;
 }
 
 extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
@@ -333,9 +387,17 @@ extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, 
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
   const int rpb = rows_per_block_host(C);
   k_bn_stats<<<L.blocks, L.threads, 3 * L.threads * sizeof(float), st>>>(x, ldx, n_cap, n_dev, C, L.RL, rpb, part);
+  const float* part_apply = part;
+  int blocks_apply = L.blocks, rpb_apply = rpb;
+  if (L.blocks > kMergeAbove) {
+    float* merged = part + (int64_t)L.blocks * 3 * C;
+    k_bn_merge_stats<<<1, L.threads, 3 * L.threads * sizeof(float), st>>>(part, n_cap, n_dev, C, L.RL, rpb, L.blocks, merged);
+    part_apply = merged; blocks_apply = 1; rpb_apply = 1 << 30;
+    count_launches(1);
+  }
   k_bn_apply_train<<<apply_grid(n_cap, L.RL), L.threads, 3 * L.threads * sizeof(float), st>>>(
-      x, ldx, n_cap, n_dev, C, L.RL, rpb, L.blocks, part, gamma, beta, running_mean, running_var, eps, retention, leak,
-      y, ldy, save_mean, save_invstd);
+      x, ldx, n_cap, n_dev, C, L.RL, rpb_apply, blocks_apply, part_apply, gamma, beta, running_mean, running_var, eps,
+      retention, leak, y, ldy, save_mean, save_invstd);
   count_launches(2);
   B200_CHECK_LAUNCH("bn_fwd_train");
   return 0;
@@ -374,9 +436,17 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
   k_bn_bwd_reduce<<<L.blocks, L.threads, 2 * L.threads * sizeof(float), st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL,
                                                                               rpb, gamma, beta, mean, invstd, leak,
                                                                               part);
+  const float* part_apply = part;
+  int blocks_apply = L.blocks, rpb_apply = rpb;
+  if (L.blocks > kMergeAbove) {
+    float* merged = part + (int64_t)L.blocks * 3 * C;
+    k_bn_merge_sums<<<1, L.threads, 2 * L.threads * sizeof(float), st>>>(part, n_cap, n_dev, C, L.RL, rpb, L.blocks, merged);
+    part_apply = merged; blocks_apply = 1; rpb_apply = 1 << 30;
+    count_launches(1);
+  }
   k_bn_bwd_apply<<<apply_grid(n_cap, L.RL), L.threads, 2 * L.threads * sizeof(float), st>>>(
-      x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, rpb, L.blocks, part, gamma, beta, mean, invstd, leak, train, dgamma,
-      dbeta, dx, lddx);
+      x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, rpb_apply, blocks_apply, part_apply, gamma, beta, mean, invstd, leak, train,
+      dgamma, dbeta, dx, lddx);
   count_launches(2);
   B200_CHECK_LAUNCH("bn_bwd");
   return 0;

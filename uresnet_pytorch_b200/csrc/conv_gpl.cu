@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   // memory, low parts recomputed) only when the offset changes -- the L1/shared data pipe is this
   // kernel's bottleneck (profiles/README.md), and the weights were a third of its shared-memory traffic
   constexpr bool WREG = WSMEM && (Q * MT <= 2);
-  constexpr bool WLO = WSMEM && X3 && !WREG;  // separate low-part copy in shared memory
+  constexpr bool WLO = false;  // (no separate low-part copy: shared memory holds raw fp32, low parts are recomputed)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   float4* const acc = reinterpret_cast<float4*>(smem_raw + acc_base + warp * kAccBytes);
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t s_acc = s_base + acc_base + warp * kAccBytes + t * 8;  // + row * CT * 4 + chunk * 32
-  const uint32_t s_whi = s_base + lane * 16, s_wlo = s_whi + w_elems * 4;
+  const uint32_t s_whi = s_base + lane * 16;
   const uint32_t s_ring = s_base + acc_base + warps * kAccBytes + warp * (kRecRing * 128);
 
   if (WSMEM) {
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       const int mt = col >> 4, odd = (col >> 3) & 1, gg = col & 7;
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + odd * 2 + (rem & 1);
       const float hi = tf32_hi(v);
-      Whi[dst] = WREG ? v : hi;
-      if (WLO) Wlo[dst] = v - hi;
+      (void)hi; (void)Wlo;
+      Whi[dst] = v;  // raw fp32: the tensor core truncates the high part itself, the low part is recomputed
     }
     __syncthreads();
   }
@@ -396,12 +396,11 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
                 }
               } else if (WSMEM) {
                 const float4 b4 = lds128(s_whi + wk_off + (s * MT + mt) * 512);
-                bh[0][0] = __float_as_uint(b4.x); bh[0][1] = __float_as_uint(b4.y);
-                bh[1][0] = __float_as_uint(b4.z); bh[1][1] = __float_as_uint(b4.w);
-                if (X3) {
-                  const float4 l4 = lds128(s_wlo + wk_off + (s * MT + mt) * 512);
-                  bl[0][0] = __float_as_uint(l4.x); bl[0][1] = __float_as_uint(l4.y);
-                  bl[1][0] = __float_as_uint(l4.z); bl[1][1] = __float_as_uint(l4.w);
+                const float w4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  bh[r >> 1][r & 1] = __float_as_uint(w4[r]);
+                  if (X3) bl[r >> 1][r & 1] = __float_as_uint(w4[r] - tf32_hi(w4[r]));
                 }
               } else {
                 const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
@@ -648,11 +647,10 @@ __global__ void __launch_bounds__(512) k_conv_gpl_small(const GplParams p) {
 }
 
 size_t acc_bytes(int R, int mt) { return (size_t)(R + 1) * (16 * mt) * 4; }
-// shared-memory weight copy of k_conv_gpl: raw fp32 when the fragments are register-cached
-// (Q * MT <= 2, see WREG), else separate high and low parts for tf32x3
+// shared-memory weight copy of k_conv_gpl: raw fp32 (low parts of the tf32x3 split are recomputed)
 size_t w_smem_bytes(int K, int Cin, int mt, int x3) {
-  const bool wreg = (Cin / 16) * mt <= 2;
-  return (size_t)K * Cin * 16 * mt * 4 * ((x3 && !wreg) ? 2 : 1);
+  (void)x3;
+  return (size_t)K * Cin * 16 * mt * 4;
 }
 
 int large_warps() {
@@ -901,6 +899,8 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
     const char* e = getenv("B200SCN_GPL_LARGE_MIN_ROWS");
     large_min = e ? atoll(e) : (int64_t)128 * 8 * sm_count();
   }
+  // (wider inputs take the small-input kernel below, which walks any Cin in one launch: measured equal on
+  // the 768^3 / uf=32 configuration, with a third fewer launches)
   const bool large = tile_rows == 128 && tile_end == nullptr && Cin <= 64 && n_out_cap >= large_min;
   if (large) {
     int MT = 0;
