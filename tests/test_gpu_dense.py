@@ -125,3 +125,32 @@ def test_dense_batchnorm_matches_torch():
     yr.backward(go)
     y.backward(go.permute(0, 2, 3, 4, 1).contiguous().cuda())
     assert rel_l2(xg.grad.permute(0, 4, 1, 2, 3), xr.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("kind,dims,k,stride,cin,cout", [
+    ("conv", 3, 3, 1, 32, 32), ("conv", 3, 3, 2, 64, 48), ("conv", 2, 3, 1, 32, 16), ("conv", 3, 1, 2, 96, 32),
+    ("convT", 3, 3, 2, 64, 32), ("conv", 3, 3, 1, 32, 272)])
+def test_dense_conv_tcgen05_matches_ffma(kind, dims, k, stride, cin, cout):
+    """csrc/dense_tc.cu (tcgen05.mma kind::tf32, TMEM accumulators, implicit-GEMM gather) against the exact-fp32
+    FFMA kernel on the same module: forward and input gradient, single-pass TF32 tolerance."""
+    import subprocess
+    import sys
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.dense import Conv, ConvTranspose
+    torch.manual_seed(3)
+    size = 9 if kind == "conv" else 5
+    mod = (Conv(dims, cin, cout, k, stride) if kind == "conv" else ConvTranspose(dims, cin, cout)).cuda()
+    shape = (2,) + ((size,) * 3 if dims == 3 else (1, size, size)) + (cin,)
+    x0 = torch.randn(shape, device="cuda")
+    outs, grads = [], []
+    for mode in (scn.MATH_FP32, scn.MATH_TF32):
+        x = x0.clone().requires_grad_(True)
+        with scn.math(mode):
+            y = mod(x)
+            (y * torch.linspace(-1, 1, y.numel(), device="cuda").reshape(y.shape)).sum().backward()
+        torch.cuda.synchronize()
+        outs.append(y.detach())
+        grads.append(x.grad.detach())
+    assert outs[0].shape == outs[1].shape
+    assert (outs[0] - outs[1]).abs().max().item() <= 5e-3 * outs[0].abs().max().item()
+    assert (grads[0] - grads[1]).abs().max().item() <= 5e-3 * grads[0].abs().max().item()

@@ -124,6 +124,9 @@ inline int64_t out_rows(const DenseGeom& g, int batch) {
 }
 
 }  // namespace
+
+int read_geom_public(const int32_t* g, DenseGeom* out) { return read_geom(g, out); }
+
 }  // namespace b200scn
 
 using namespace b200scn;

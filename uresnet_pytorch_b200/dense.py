@@ -67,6 +67,21 @@ class _PadReplicate(torch.autograd.Function):
         return din, None, None, None
 
 
+def _conv_call(x_ptr, Cin, w_ptr, w_si, w_so, bias, g, B, Cout, out, T, device):
+    """One dense convolution launch: the tcgen05 implicit-GEMM kernel (csrc/dense_tc.cu) in the single-pass TF32
+    math mode when the channel counts allow, else the exact-fp32 FFMA kernel."""
+    from .sparseconvnet import config
+    if config.math_mode == config.MATH_TF32 and Cin % 32 == 0 and Cout % 16 == 0:
+        L = _lib.load()
+        nbytes = L.b200scn_dense_conv_tc_scratch_bytes(T, Cin, Cout)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.call("b200scn_dense_conv_tc", x_ptr, Cin, w_ptr, 1, w_si, w_so, _lib.ptr(bias), g, B, Cin, Cout,
+                  out.data_ptr(), Cout, scratch.data_ptr(), nbytes, _stream())
+        return
+    _lib.call("b200scn_dense_conv", x_ptr, Cin, w_ptr, 1, w_si, w_so, _lib.ptr(bias), g, B, Cin, Cout, out.data_ptr(),
+              Cout, _stream())
+
+
 class _DenseConv(torch.autograd.Function):
     """nn.Conv{2,3}d(padding=0) / nn.ConvTranspose{2,3}d(padding, output_padding) on channels-last data."""
 
@@ -90,8 +105,7 @@ class _DenseConv(torch.autograd.Function):
             mode, w_si, w_so = 1, T, Cin * T
         out = torch.empty([B] + out_sz + [Cout], dtype=torch.float32, device=x.device)
         g = _geom(mode, dims, in_sz, out_sz, k, stride, pad)
-        _lib.call("b200scn_dense_conv", x.data_ptr(), Cin, w.data_ptr(), 1, w_si, w_so, _lib.ptr(bias), g, B, Cin, Cout,
-                  out.data_ptr(), Cout, _stream())
+        _conv_call(x.data_ptr(), Cin, w.data_ptr(), w_si, w_so, bias, g, B, Cout, out, T, x.device)
         ctx.save_for_backward(x, w)
         ctx.cfg = (k, stride, transposed, pad, dims, in_sz, out_sz, Cin, Cout, bias is not None, tuple(weight.shape))
         return out
@@ -112,8 +126,7 @@ class _DenseConv(torch.autograd.Function):
             # the transpose of the forward index map, over the *input* grid, with W^T
             dx = torch.empty([B] + in_sz + [Cin], dtype=torch.float32, device=x.device)
             g = _geom(1 if transposed else 2, dims, out_sz, in_sz, k, stride, pad)
-            _lib.call("b200scn_dense_conv", dout.data_ptr(), Cout, w.data_ptr(), 1, w_so, w_si, None, g, B, Cout, Cin,
-                      dx.data_ptr(), Cin, _stream())
+            _conv_call(dout.data_ptr(), Cout, w.data_ptr(), w_so, w_si, None, g, B, Cin, dx, T, x.device)
         if ctx.needs_input_grad[1]:
             g = _geom(2 if transposed else 1, dims, in_sz, out_sz, k, stride, pad)
             nbytes = L.b200scn_dense_wgrad_scratch_bytes(g, B, Cin, Cout)
