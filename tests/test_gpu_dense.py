@@ -143,7 +143,7 @@ def test_dense_conv_tcgen05_matches_ffma(kind, dims, k, stride, cin, cout):
     shape = (2,) + ((size,) * 3 if dims == 3 else (1, size, size)) + (cin,)
     x0 = torch.randn(shape, device="cuda")
     outs, grads = [], []
-    for mode in (scn.MATH_FP32, scn.MATH_TF32):
+    for mode in (scn.MATH_FP32, scn.MATH_TF32, scn.MATH_TF32X3):
         x = x0.clone().requires_grad_(True)
         with scn.math(mode):
             y = mod(x)
@@ -151,6 +151,9 @@ def test_dense_conv_tcgen05_matches_ffma(kind, dims, k, stride, cin, cout):
         torch.cuda.synchronize()
         outs.append(y.detach())
         grads.append(x.grad.detach())
-    assert outs[0].shape == outs[1].shape
+    assert outs[0].shape == outs[1].shape == outs[2].shape
     assert (outs[0] - outs[1]).abs().max().item() <= 5e-3 * outs[0].abs().max().item()
     assert (grads[0] - grads[1]).abs().max().item() <= 5e-3 * grads[0].abs().max().item()
+    # 3xTF32 is fp32-equivalent: the tolerance of the FFMA-vs-torch layer tests
+    assert (outs[0] - outs[2]).abs().max().item() <= 3e-5 * outs[0].abs().max().item()
+    assert (grads[0] - grads[2]).abs().max().item() <= 3e-5 * grads[0].abs().max().item()

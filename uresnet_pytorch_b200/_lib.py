@@ -34,7 +34,8 @@ SIGNATURES = {
                                 _I32, _P, _I64, _I32, _I32, _P]),
     "b200scn_pack_weights": (_I32, [_P, _I32, _I64, _P]),
     "b200scn_dense_conv_tc_scratch_bytes": (_I64, [_I32, _I32, _I32]),
-    "b200scn_dense_conv_tc": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _P, _I64, _P]),
+    "b200scn_dense_conv_tc": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _I32, _P, _I64,
+                                     _P]),
     "b200scn_adam_step": (_I32, [_P, _I32, _I64, _P, _P, _F32, _F32, _F32, _F32, _P]),
     "b200scn_head_loss_scratch_bytes": (_I64, [_I64, _I32, _I32, _I32]),
     "b200scn_head_loss": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I32, _I64, _I64, _P, _I32, _I32, _I32, _P,

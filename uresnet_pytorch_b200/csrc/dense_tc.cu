@@ -20,7 +20,6 @@
 namespace b200scn {
 namespace {
 
-constexpr int kStages = 4;
 constexpr int kBM = 128;     // output voxels per CTA (UMMA M)
 constexpr int kBK = 32;      // input channels per K block (128 B of tf32)
 constexpr int kProducers = 128;
@@ -73,7 +72,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // Wt[tap][chunk][co][32] = W[tap][32 chunk + j][co]   (K-major copy: 128 contiguous bytes per (co, chunk))
 __global__ void k_dense_pack_wt(const float* __restrict__ W, int64_t w_sk, int64_t w_si, int64_t w_so, int taps, int Cin,
-                                int Cout, float* __restrict__ Wt) {
+                                int Cout, float* __restrict__ Wt, float* __restrict__ Wt_lo) {
   const int64_t total = (int64_t)taps * Cin * Cout;
   const int chunks = Cin / kBK;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -83,13 +82,21 @@ __global__ void k_dense_pack_wt(const float* __restrict__ W, int64_t w_sk, int64
     rest /= Cout;
     const int chunk = (int)(rest % chunks);
     const int tap = (int)(rest / chunks);
-    Wt[e] = __ldg(W + tap * w_sk + (int64_t)(chunk * kBK + j) * w_si + co * w_so);
+    const float v = __ldg(W + tap * w_sk + (int64_t)(chunk * kBK + j) * w_si + co * w_so);
+    if (Wt_lo != nullptr) {  // 3xTF32: high part = truncation to tf32, low part = exact remainder
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      Wt[e] = hi;
+      Wt_lo[e] = v - hi;
+    } else {
+      Wt[e] = v;
+    }
   }
 }
 
 struct DtcParams {
   const float* in; int64_t ldi;
   const float* Wt;      // packed weights, [taps][Cin/32][Cout][32]
+  const float* Wt_lo;   // low parts (3xTF32) or NULL
   const float* bias;
   float* out; int64_t ldo;
   int64_t n_out;
@@ -99,7 +106,12 @@ struct DtcParams {
   DenseGeom geom;
 };
 
+// X3: 3xTF32 (fp32-equivalent products): D += A_lo B_hi + A_hi B_lo + A_hi B_hi.  The A rows then pass through
+// registers (LDG.128 -> split -> STS.128 into a high and a low tile, next block's row prefetched), the low
+// weight parts come from a second packed copy; 3 shared-memory stages of [A_hi | A_lo | B_hi | B_lo].
+template <bool X3>
 __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcParams p) {
+  constexpr int kStages = X3 ? 3 : 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], done_bar;
   __shared__ uint32_t tmem_base_s;
@@ -107,7 +119,8 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = p.n_pass;
   const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)N * 128;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (X3 ? 2 : 1);
+  const uint32_t a_lo_off = a_bytes, b_off = a_bytes * (X3 ? 2 : 1), b_lo_off = b_off + b_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int co0 = blockIdx.y * N;
   const int chunks = p.Cin / kBK;
@@ -134,35 +147,83 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
     const int64_t o = o0 + r;
     const uint32_t sw = (uint32_t)(r & 7);
     int cur_tap = -1, idx = -1;
-    for (int kb = 0; kb < n_kb + kLag; ++kb) {
-      if (kb < n_kb) {
-        const int s = kb % kStages;
-        mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
-        const int tap = kb / chunks, chunk = kb - tap * chunks;
-        if (tap != cur_tap) {
-          cur_tap = tap;
-          idx = o < p.n_out ? dense_index(p.geom, (int)o, tap) : -1;
-        }
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
-        const float* a_src = idx >= 0 ? p.in + (int64_t)idx * p.ldi + chunk * kBK : p.in;
-        const int nbytes = idx >= 0 ? 16 : 0;
+    auto row_of = [&](int kb) -> const float* {  // input row of block kb (nullptr: zero row)
+      const int tap = kb / chunks, chunk = kb - tap * chunks;
+      if (tap != cur_tap) {
+        cur_tap = tap;
+        idx = o < p.n_out ? dense_index(p.geom, (int)o, tap) : -1;
+      }
+      return idx >= 0 ? p.in + (int64_t)idx * p.ldi + chunk * kBK : nullptr;
+    };
+    auto copy_b = [&](int kb, int s) {
+      const int tap = kb / chunks, chunk = kb - tap * chunks;
+      const int64_t woff = ((int64_t)(tap * chunks + chunk) * p.Cout + co0) * kBK;
+      for (int n = r; n < N; n += kProducers) {
+        const uint32_t b_dst = smem_u32(smem + (size_t)s * stage_bytes + b_off) + (uint32_t)n * 128;
+        const uint32_t swn = (uint32_t)(n & 7);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp_async16_zfill(a_dst + ((j ^ sw) << 4), a_src + 4 * j, nbytes);
-        const float* wt = p.Wt + ((int64_t)(tap * chunks + chunk) * p.Cout + co0) * kBK;
-        for (int n = r; n < N; n += kProducers) {
-          const uint32_t b_dst = smem_u32(smem + (size_t)s * stage_bytes + a_bytes) + (uint32_t)n * 128;
-          const float* b_src = wt + (int64_t)n * kBK;
-          const uint32_t swn = (uint32_t)(n & 7);
+        for (int j = 0; j < 8; ++j) cp_async16_zfill(b_dst + ((j ^ swn) << 4), p.Wt + woff + (int64_t)n * kBK + 4 * j, 16);
+        if (X3) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp_async16_zfill(b_dst + ((j ^ swn) << 4), b_src + 4 * j, 16);
+          for (int j = 0; j < 8; ++j)
+            cp_async16_zfill(b_dst + b_bytes + ((j ^ swn) << 4), p.Wt_lo + woff + (int64_t)n * kBK + 4 * j, 16);
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      const int done_kb = kb - kLag;  // the copies of this block have had kLag iterations to land
-      if (done_kb >= 0) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-        mbar_arrive(&full_bar[done_kb % kStages]);
+    };
+    if (!X3) {
+      for (int kb = 0; kb < n_kb + kLag; ++kb) {
+        if (kb < n_kb) {
+          const int s = kb % kStages;
+          mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
+          const float* a_row = row_of(kb);
+          const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
+          const float* a_src = a_row ? a_row : p.in;
+          const int nbytes = a_row ? 16 : 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp_async16_zfill(a_dst + ((j ^ sw) << 4), a_src + 4 * j, nbytes);
+          copy_b(kb, s);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int done_kb = kb - kLag;  // the copies of this block have had kLag iterations to land
+        if (done_kb >= 0) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+          mbar_arrive(&full_bar[done_kb % kStages]);
+        }
+      }
+    } else {
+      float4 cur[8], nxt[8];
+      auto load_row = [&](const float* a_row, float4 (&v)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = a_row ? __ldg(reinterpret_cast<const float4*>(a_row) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_row(row_of(0), cur);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kStages;
+        if (kb + 1 < n_kb) load_row(row_of(kb + 1), nxt);  // in flight while this block is split and stored
+        mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
+        copy_b(kb, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+          float hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hi[q] = __uint_as_float(__float_as_uint(x[q]) & 0xffffe000u);
+            lo[q] = x[q] - hi[q];
+          }
+          const uint32_t d = a_dst + ((j ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(d), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(d + a_lo_off), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&full_bar[s]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
       }
     }
     // ===== epilogue: TMEM -> registers -> global; warp w reads TMEM lanes 32w .. 32w+31 =====
@@ -200,10 +261,17 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
       const int s = kb % kStages;
       mbar_wait(&full_bar[s], (kb / kStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + a_bytes;
+      const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + b_off;
 #pragma unroll
       for (int k = 0; k < kBK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
-        umma_tf32(tmem_base, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+        if (X3) {
+          umma_tf32(tmem_base, umma_desc(a_addr + a_lo_off + k * 32), umma_desc(b_addr + k * 32), idesc, first);
+          umma_tf32(tmem_base, umma_desc(a_addr + k * 32), umma_desc(a_addr + b_lo_off + k * 32), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, 1u);
+        } else {
+          umma_tf32(tmem_base, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, first);
+        }
       }
       umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
     }
@@ -225,15 +293,15 @@ int read_geom_public(const int32_t* g, DenseGeom* out);
 using namespace b200scn;
 
 extern "C" int64_t b200scn_dense_conv_tc_scratch_bytes(int taps, int Cin, int Cout) {
-  return (int64_t)taps * Cin * Cout * 4 + 256;
+  return (int64_t)2 * taps * Cin * Cout * 4 + 512;
 }
 
 /* tcgen05 implicit-GEMM variant of b200scn_dense_conv (single-pass TF32).  Needs Cin % 32 == 0, Cout % 16 == 0;
  * returns B200SCN_ERR_UNSUPPORTED otherwise (the caller falls back to b200scn_dense_conv). */
 extern "C" int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si,
                                      int64_t w_so, const float* bias, const int32_t* geom_host, int batch, int Cin,
-                                     int Cout, float* out, int64_t ldo, void* scratch, int64_t scratch_bytes,
-                                     void* stream) {
+                                     int Cout, float* out, int64_t ldo, int math_mode, void* scratch,
+                                     int64_t scratch_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DenseGeom g;
   if (int rc = read_geom_public(geom_host, &g)) return rc;
@@ -246,33 +314,42 @@ extern "C" int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* 
   B200_CHECK_ARG(scratch_bytes >= b200scn_dense_conv_tc_scratch_bytes(taps, Cin, Cout), "dense_conv_tc: scratch too small");
   const int64_t n = (int64_t)batch * g.out_sz[0] * g.out_sz[1] * g.out_sz[2];
   B200_CHECK_ARG(n < (1ll << 31) && n >= 1, "dense_conv_tc: bad voxel count");
+  B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "dense_conv_tc: tensor-core math modes only");
+  const bool x3 = math_mode == B200SCN_MATH_TF32X3;
+  const int64_t total = (int64_t)taps * Cin * Cout;
   float* Wt = reinterpret_cast<float*>(scratch);
+  float* Wt_lo = x3 ? Wt + ((total + 63) / 64) * 64 : nullptr;
   {
-    const int64_t total = (int64_t)taps * Cin * Cout;
     int64_t gsz = cdiv(total, 256);
     if (gsz > 2048) gsz = 2048;
-    k_dense_pack_wt<<<(int)gsz, 256, 0, st>>>(W, w_sk, w_si, w_so, taps, Cin, Cout, Wt);
+    k_dense_pack_wt<<<(int)gsz, 256, 0, st>>>(W, w_sk, w_si, w_so, taps, Cin, Cout, Wt, Wt_lo);
   }
-  // passes over the output channels: the largest multiple of 16 <= 256 that divides Cout
+  // passes over the output channels: the largest multiple of 16 <= 256 (128 with the doubled 3xTF32 tiles)
+  // that divides Cout
+  const int n_max = x3 ? 128 : 256;
   int n_pass = Cout;
-  if (n_pass > 256) {
-    n_pass = 256;
+  if (n_pass > n_max) {
+    n_pass = n_max;
     while (Cout % n_pass != 0) n_pass -= 16;
   }
   DtcParams p;
-  p.in = in; p.ldi = ldi; p.Wt = Wt; p.bias = bias; p.out = out; p.ldo = ldo; p.n_out = n; p.Cin = Cin; p.Cout = Cout;
+  p.in = in; p.ldi = ldi; p.Wt = Wt; p.Wt_lo = Wt_lo; p.bias = bias; p.out = out; p.ldo = ldo; p.n_out = n; p.Cin = Cin; p.Cout = Cout;
   p.taps = taps; p.n_pass = n_pass; p.geom = g;
   uint32_t cols = 32;
   while ((int)cols < n_pass) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = (size_t)kStages * (kBM * 128 + (size_t)n_pass * 128) + 1024;
+  const size_t smem = (size_t)(x3 ? 3 * 2 : 4) * (kBM * 128 + (size_t)n_pass * 128) + 1024;
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_dense_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(k_dense_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(k_dense_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   dim3 grid((unsigned)cdiv(n, kBM), (unsigned)(Cout / n_pass));
-  k_dense_conv_tc<<<grid, kProducers + 32, smem, st>>>(p);
+  if (x3)
+    k_dense_conv_tc<true><<<grid, kProducers + 32, smem, st>>>(p);
+  else
+    k_dense_conv_tc<false><<<grid, kProducers + 32, smem, st>>>(p);
   count_launches(2);
   B200_CHECK_LAUNCH("dense_conv_tc");
   return 0;

@@ -68,15 +68,16 @@ class _PadReplicate(torch.autograd.Function):
 
 
 def _conv_call(x_ptr, Cin, w_ptr, w_si, w_so, bias, g, B, Cout, out, T, device):
-    """One dense convolution launch: the tcgen05 implicit-GEMM kernel (csrc/dense_tc.cu) in the single-pass TF32
-    math mode when the channel counts allow, else the exact-fp32 FFMA kernel."""
+    """One dense convolution launch: the tcgen05 implicit-GEMM kernel (csrc/dense_tc.cu) in the tensor-core
+    math modes (tf32x3 = fp32-equivalent, tf32 = single pass) when the channel counts allow, else the
+    exact-fp32 FFMA kernel."""
     from .sparseconvnet import config
-    if config.math_mode == config.MATH_TF32 and Cin % 32 == 0 and Cout % 16 == 0:
+    if config.math_mode != config.MATH_FP32 and Cin % 32 == 0 and Cout % 16 == 0:
         L = _lib.load()
         nbytes = L.b200scn_dense_conv_tc_scratch_bytes(T, Cin, Cout)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _lib.call("b200scn_dense_conv_tc", x_ptr, Cin, w_ptr, 1, w_si, w_so, _lib.ptr(bias), g, B, Cin, Cout,
-                  out.data_ptr(), Cout, scratch.data_ptr(), nbytes, _stream())
+                  out.data_ptr(), Cout, config.math_mode, scratch.data_ptr(), nbytes, _stream())
         return
     _lib.call("b200scn_dense_conv", x_ptr, Cin, w_ptr, 1, w_si, w_so, _lib.ptr(bias), g, B, Cin, Cout, out.data_ptr(),
               Cout, _stream())
