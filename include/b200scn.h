@@ -196,6 +196,23 @@ int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, i
                    const float* invstd, float leak, int train, float* dx, int64_t lddx, float* dgamma,
                    float* dbeta, void* scratch, int64_t scratch_bytes, void* stream);
 
+/* Single-launch variants for inputs small enough to sit in the SMs' registers (every level of a bs=1 512^3
+ * event): statistics, a grid-wide barrier and the apply phase in ONE co-resident grid (<= one CTA per SM), so
+ * the matrix is read once and the second launch disappears.  `sync` = two uint32 of caller-owned device memory,
+ * zero before the first use (barrier count + generation; every call leaves the count at zero), not shared by
+ * calls that may run concurrently; NULL, or an input too large (judged from n_expect, the rows a typical event
+ * holds at this level, 0 = unknown), falls through to the two-kernel functions above.  Same results contract. */
+int b200scn_bn_fwd_train_sync(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int64_t n_expect,
+                              int C, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float eps, float retention, float leak, float* y, int64_t ldy,
+                              float* save_mean, float* save_invstd, uint32_t* sync, void* scratch,
+                              int64_t scratch_bytes, void* stream);
+int b200scn_bn_bwd_sync(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t n_cap,
+                        const int32_t* n_dev, int64_t n_expect, int C, const float* gamma, const float* beta,
+                        const float* mean, const float* invstd, float leak, int train, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, uint32_t* sync, void* scratch, int64_t scratch_bytes,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (iv) input / output layers -- scn.InputLayer features (mode 3 sums) and scn.OutputLayer
  * (uresnet_sparse.py:20,24), forward and backward.

@@ -143,6 +143,45 @@ def test_batchnorm_large_mean_is_stable():
     assert (y.cpu().double() - ref).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize("n,c,live", [(1, 16, None), (37, 1, None), (1362, 128, None), (23000, 32, None),
+                                      (32768, 16, 9405), (32768, 64, 3987), (40000, 48, None), (6000, 320, 1017),
+                                      (300000, 32, None)])
+def test_batchnorm_single_launch_matches_two_kernel(n, c, live):
+    """The single-launch kernels (grid barrier, csrc/bnrelu.cu) against the two-kernel path and an fp64 torch
+    restatement; the same barrier words are reused by every call (count must return to zero each time)."""
+    from uresnet_pytorch_b200.sparseconvnet import functional as F
+    torch.manual_seed(n + c)
+    x = (torch.randn(n, c, device="cuda") * 1.5 + 0.7)
+    dy = torch.randn(n, c, device="cuda")
+    w = torch.rand(c, device="cuda") + 0.5
+    b = torch.rand(c, device="cuda") - 0.5
+    n_dev = torch.tensor([live], dtype=torch.int32, device="cuda") if live is not None else None
+    m = live if live is not None else n
+    sync = torch.zeros(2, dtype=torch.int32, device="cuda")
+    res = []
+    for sy in (None, sync, sync, sync):
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        xx = x.clone().requires_grad_(True)
+        ww, bb = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = F.BatchNormAct.apply(xx, ww, bb, rm, rv, 1e-4, 0.9, 0.0, True, n,
+                                 n_dev.data_ptr() if n_dev is not None else None, sy, m if live is not None else 0)
+        y[:m].backward(dy[:m])
+        torch.cuda.synchronize()
+        res.append((y.detach()[:m], xx.grad[:m], ww.grad, bb.grad, rm, rv))
+    assert int(sync[0].item()) == 0 and int(sync[1].item()) in (0, 6)  # 3 forward + 3 backward barriers, or fallback
+    xd = x[:m].double()
+    mu, var = xd.mean(0), xd.var(0, unbiased=False)
+    ref = torch.relu((xd - mu) / (var + 1e-4).sqrt() * w.double() + b.double())
+    for r in res:
+        assert (r[0].double() - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1.0)
+    for r in res[1:]:
+        for a, o in zip(r, res[0]):
+            assert rel_l2(a, o) <= 2e-5
+    # run-to-run determinism of the single-launch path
+    for a, o in zip(res[1], res[2]):
+        assert torch.equal(a, o)
+
+
 def test_input_output_layers_with_duplicates():
     from uresnet_pytorch_b200 import sparseconvnet as scn
     x_o, x_g, f_o, f_g = _pair(3, 16, dup=120, nfeat=3)

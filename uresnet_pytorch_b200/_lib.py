@@ -53,6 +53,10 @@ SIGNATURES = {
     "b200scn_bn_fwd_eval": (_I32, [_P, _I64, _I64, _P, _I32, _P, _P, _P, _P, _F32, _F32, _P, _I64, _P]),
     "b200scn_bn_bwd": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I32, _P, _P, _P, _P, _F32, _I32, _P, _I64, _P, _P, _P,
                               _I64, _P]),
+    "b200scn_bn_fwd_train_sync": (_I32, [_P, _I64, _I64, _P, _I64, _I32, _P, _P, _P, _P, _F32, _F32, _F32, _P, _I64, _P,
+                                         _P, _P, _P, _I64, _P]),
+    "b200scn_bn_bwd_sync": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I64, _I32, _P, _P, _P, _P, _F32, _I32, _P, _I64, _P,
+                                   _P, _P, _P, _I64, _P]),
     "b200scn_gather_rows": (_I32, [_P, _I64, _P, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_segsum_rows": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_add_rows": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I32, _P, _I64, _P]),

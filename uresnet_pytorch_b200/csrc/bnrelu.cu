@@ -355,6 +355,279 @@ __global__ void k_bn_merge_sums(const float* __restrict__ part, int64_t n_cap, c
   }
 }
 
+
+// ---- single-launch variants for inputs that fit the SMs' registers (every level of a bs=1 512^3 event) ------
+// One co-resident grid (<= one CTA per SM): statistics, a grid-wide barrier, then the apply phase on the SAME
+// registers -- the feature matrix is read once and the second launch (5-9 us of pure latency per layer at these
+// sizes) disappears.  The barrier state (count, generation) lives in caller memory that is zero before the first
+// use and is left zero-count by every launch; all CTAs are resident at once because the grid never exceeds the
+// SM count, so the spin cannot starve a CTA that has not started.
+constexpr int kFusedV = 8;  // values per thread cached in registers; rows beyond are re-read (L2 hits)
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* sync, unsigned int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = ld_acquire_u32(sync + 1);
+    __threadfence();
+    const unsigned int old = atomicAdd(sync, 1u);
+    if (old == G - 1u) {
+      sync[0] = 0u;  // ready for the next launch
+      __threadfence();
+      atomicAdd(sync + 1, 1u);
+    } else {
+      while (ld_acquire_u32(sync + 1) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_bn_fwd_fused(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const int32_t* __restrict__ n_dev, int C, int RL,
+               float* __restrict__ part, unsigned int* sync, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float* running_mean, float* running_var, float eps, float retention,
+               float leak, float* __restrict__ y, int64_t ldy, float* __restrict__ save_mean,
+               float* __restrict__ save_invstd) {
+  extern __shared__ float sm[];  // [3][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int G = (int)gridDim.x;
+  const int rpb = (n + G - 1) / G;
+  const int r0 = min(n, (int)blockIdx.x * rpb), r1 = min(n, r0 + rpb);
+
+  float xv[kFusedV];
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    const int r = r0 + rl + v * RL;
+    xv[v] = r < r1 ? __ldg(x + (int64_t)r * ldx + c) : 0.f;
+  }
+  float cnt = 0.f, s1 = 0.f, s2 = 0.f;
+  const float shift0 = xv[0];
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    if (r0 + rl + v * RL < r1) {
+      const float d = xv[v] - shift0;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+      cnt += 1.f;
+    }
+  }
+  for (int r = r0 + rl + kFusedV * RL; r < r1; r += RL) {
+    const float d = __ldg(x + (int64_t)r * ldx + c) - shift0;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+    cnt += 1.f;
+  }
+  float mean = 0.f, m2 = 0.f;
+  if (cnt > 0.f) {
+    mean = shift0 + s1 / cnt;
+    m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+  }
+  sm[t] = cnt;
+  sm[T + t] = mean;
+  sm[2 * T + t] = m2;
+  chan_tree_merge(sm, T, C, RL, c, rl);
+  if (rl == 0) {
+    float* p = part + (int64_t)blockIdx.x * 3 * C;
+    p[c] = sm[c];
+    p[C + c] = sm[T + c];
+    p[2 * C + c] = sm[2 * T + c];
+  }
+  grid_barrier(sync, (unsigned int)G);
+  {
+    float N = 0.f, M = 0.f, S = 0.f;
+    int b = rl;
+    for (; b + 3 * RL < G; b += 4 * RL) {
+      float pn[4], pm[4], ps[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = part + (int64_t)(b + u * RL) * 3 * C;
+        pn[u] = __ldcg(p + c); pm[u] = __ldcg(p + C + c); ps[u] = __ldcg(p + 2 * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) chan_merge(N, M, S, pn[u], pm[u], ps[u]);
+    }
+    for (; b < G; b += RL) {
+      const float* p = part + (int64_t)b * 3 * C;
+      chan_merge(N, M, S, __ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c));
+    }
+    __syncthreads();  // chan_tree_merge above left readers of sm[] behind the barrier only; be explicit
+    sm[t] = N;
+    sm[T + t] = M;
+    sm[2 * T + t] = S;
+  }
+  chan_tree_merge(sm, T, C, RL, c, rl);
+  const float N = sm[c], M = sm[T + c], S = sm[2 * T + c];
+  const float is = rsqrtf((N > 0.f ? S / N : 0.f) + eps);
+  if (blockIdx.x == 0 && rl == 0) {
+    save_mean[c] = M;
+    save_invstd[c] = is;
+    if (running_mean != nullptr) {
+      running_mean[c] = retention * running_mean[c] + (1.f - retention) * M;
+      running_var[c] = retention * running_var[c] + (1.f - retention) * (S / fmaxf(N - 1.f, 1.f));
+    }
+  }
+  const float g = gamma ? gamma[c] : 1.f, bb = beta ? beta[c] : 0.f;
+  const float scale = is * g;
+  const float shift = bb - M * scale;
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    const int r = r0 + rl + v * RL;
+    if (r < r1) {
+      float o = fmaf(xv[v], scale, shift);
+      o = o > 0.f ? o : o * leak;
+      y[(int64_t)r * ldy + c] = o;
+    }
+  }
+  for (int r = r0 + rl + kFusedV * RL; r < r1; r += RL) {
+    float o = fmaf(__ldg(x + (int64_t)r * ldx + c), scale, shift);
+    o = o > 0.f ? o : o * leak;
+    y[(int64_t)r * ldy + c] = o;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_bn_bwd_fused(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy, int64_t n_cap,
+               const int32_t* __restrict__ n_dev, int C, int RL, float* __restrict__ part, unsigned int* sync,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ invstd, float leak, int train, float* __restrict__ dgamma,
+               float* __restrict__ dbeta, float* __restrict__ dx, int64_t lddx) {
+  extern __shared__ float sm[];  // [2][threads]
+  const int n = live_rows(n_dev, n_cap);
+  const int t = threadIdx.x, T = blockDim.x;
+  const int c = t % C, rl = t / C;
+  const int G = (int)gridDim.x;
+  const int rpb = (n + G - 1) / G;
+  const int r0 = min(n, (int)blockIdx.x * rpb), r1 = min(n, r0 + rpb);
+  const float mu = mean[c], is = invstd[c];
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+
+  float xh[kFusedV], dv[kFusedV];
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    const int r = r0 + rl + v * RL;
+    const bool in = r < r1;
+    xh[v] = in ? __ldg(x + (int64_t)r * ldx + c) : 0.f;
+    dv[v] = in ? __ldg(dy + (int64_t)r * lddy + c) : 0.f;
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    xh[v] = (xh[v] - mu) * is;
+    const float yv = fmaf(xh[v], g, b);
+    dv[v] = yv > 0.f ? dv[v] : dv[v] * leak;
+    if (r0 + rl + v * RL < r1) {
+      s1 += dv[v];
+      s2 = fmaf(dv[v], xh[v], s2);
+    }
+  }
+  for (int r = r0 + rl + kFusedV * RL; r < r1; r += RL) {
+    const float h = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
+    const float yv = fmaf(h, g, b);
+    float d = __ldg(dy + (int64_t)r * lddy + c);
+    d = yv > 0.f ? d : d * leak;
+    s1 += d;
+    s2 = fmaf(d, h, s2);
+  }
+  sm[t] = s1;
+  sm[T + t] = s2;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < RL; ++j) {
+      s1 += sm[j * C + c];
+      s2 += sm[T + j * C + c];
+    }
+    float* p = part + (int64_t)blockIdx.x * 2 * C;
+    p[c] = s1;
+    p[C + c] = s2;
+  }
+  grid_barrier(sync, (unsigned int)G);
+  {
+    float a1 = 0.f, a2 = 0.f;
+    int bk = rl;
+    for (; bk + 3 * RL < G; bk += 4 * RL) {
+      float v1[4], v2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = part + (int64_t)(bk + u * RL) * 2 * C;
+        v1[u] = __ldcg(p + c); v2[u] = __ldcg(p + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a1 += v1[u]; a2 += v2[u]; }
+    }
+    for (; bk < G; bk += RL) {
+      const float* p = part + (int64_t)bk * 2 * C;
+      a1 += __ldcg(p + c);
+      a2 += __ldcg(p + C + c);
+    }
+    sm[t] = a1;
+    sm[T + t] = a2;
+  }
+  __syncthreads();
+  float a1 = sm[c], a2 = sm[T + c];
+  for (int j = 1; j < RL; ++j) {
+    a1 += sm[j * C + c];
+    a2 += sm[T + j * C + c];
+  }
+  if (blockIdx.x == 0 && rl == 0) {
+    dbeta[c] = a1;
+    dgamma[c] = a2;
+  }
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  const float k1 = train ? a1 * inv_n : 0.f;
+  const float k2 = train ? a2 * inv_n : 0.f;
+  const float gi = g * is;
+#pragma unroll
+  for (int v = 0; v < kFusedV; ++v) {
+    const int r = r0 + rl + v * RL;
+    if (r < r1) dx[(int64_t)r * lddx + c] = gi * (dv[v] - k1 - xh[v] * k2);
+  }
+  for (int r = r0 + rl + kFusedV * RL; r < r1; r += RL) {
+    const float h = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
+    const float yv = fmaf(h, g, b);
+    float d = __ldg(dy + (int64_t)r * lddy + c);
+    d = yv > 0.f ? d : d * leak;
+    dx[(int64_t)r * lddx + c] = gi * (d - k1 - h * k2);
+  }
+}
+
+// Grid of the single-launch variants, or 0 when the input is too large for them (two-kernel path).
+// n_expect: rows a typical event holds at this level (0 = unknown: use the capacity).
+int fused_grid(int64_t n_cap, int64_t n_expect, int C, const Layout& L) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("B200SCN_BN_FUSED");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (!enabled) return 0;
+  int64_t rows = n_expect > 0 && n_expect < n_cap ? n_expect : n_cap;
+  const int64_t elems = rows * C;
+  const int sms = sm_count();
+  // beyond 2x the register-cached capacity the re-reads cost more than the second launch
+  if (elems > (int64_t)sms * L.threads * kFusedV * 2 || n_cap * C > (int64_t)sms * L.threads * kFusedV * 8) return 0;
+  static int vpt = 0, maxg = 0;  // values per thread the grid is sized for; CTA cap (barrier and fold cost grow with it)
+  if (vpt == 0) {
+    const char* e = getenv("B200SCN_BN_FUSED_VPT");
+    vpt = e ? atoi(e) : 8;
+    if (vpt < 1) vpt = 1;
+    e = getenv("B200SCN_BN_FUSED_MAXG");
+    maxg = e ? atoi(e) : 64;  // measured: 64 CTAs beat 148 (profiles/README.md)
+    if (maxg < 1 || maxg > sms) maxg = sms;
+  }
+  int64_t g = cdiv(elems, (int64_t)L.threads * vpt);
+  if (g > maxg) g = maxg;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 constexpr int kMergeAbove = 64;  // partial blocks beyond which the merge runs as its own launch
 
 int apply_grid(int64_t n_cap, int RL) {
@@ -372,7 +645,8 @@ using namespace b200scn;
 
 extern "C" int64_t b200scn_bn_scratch_bytes(int64_t n_cap, int C) {
   Layout L = make_layout(n_cap < 1 ? 1 : n_cap, C < 1 ? 1 : C);
-  return 256 + (int64_t)(L.blocks + 1) * 3 * C * 4;
+  const int64_t blocks = L.blocks + 1 > sm_count() ? L.blocks + 1 : sm_count();  // single-launch path: one per SM
+  return 256 + blocks * 3 * C * 4;
 }
 
 extern "C" int b200scn_bn_fwd_train(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int C,
@@ -449,5 +723,50 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
       dgamma, dbeta, dx, lddx);
   count_launches(2);
   B200_CHECK_LAUNCH("bn_bwd");
+  return 0;
+}
+
+extern "C" int b200scn_bn_fwd_train_sync(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int64_t n_expect,
+                                         int C, const float* gamma, const float* beta, float* running_mean,
+                                         float* running_var, float eps, float retention, float leak, float* y,
+                                         int64_t ldy, float* save_mean, float* save_invstd, uint32_t* sync,
+                                         void* scratch, int64_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
+  B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_fwd_train: scratch too small");
+  if (n_cap == 0) return 0;
+  Layout L = make_layout(n_cap, C);
+  const int G = sync != nullptr ? fused_grid(n_cap, n_expect, C, L) : 0;
+  if (G == 0)
+    return b200scn_bn_fwd_train(x, ldx, n_cap, n_dev, C, gamma, beta, running_mean, running_var, eps, retention, leak,
+                                y, ldy, save_mean, save_invstd, scratch, scratch_bytes, stream);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
+  k_bn_fwd_fused<<<G, L.threads, 3 * L.threads * sizeof(float), st>>>(x, ldx, n_cap, n_dev, C, L.RL, part, sync, gamma,
+                                                                      beta, running_mean, running_var, eps, retention,
+                                                                      leak, y, ldy, save_mean, save_invstd);
+  count_launches(1);
+  B200_CHECK_LAUNCH("bn_fwd_train_sync");
+  return 0;
+}
+
+extern "C" int b200scn_bn_bwd_sync(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t n_cap,
+                                   const int32_t* n_dev, int64_t n_expect, int C, const float* gamma, const float* beta,
+                                   const float* mean, const float* invstd, float leak, int train, float* dx,
+                                   int64_t lddx, float* dgamma, float* dbeta, uint32_t* sync, void* scratch,
+                                   int64_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
+  B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_bwd: scratch too small");
+  Layout L = make_layout(n_cap < 1 ? 1 : n_cap, C);
+  const int G = (sync != nullptr && n_cap > 0) ? fused_grid(n_cap, n_expect, C, L) : 0;
+  if (G == 0)
+    return b200scn_bn_bwd(x, ldx, dy, lddy, n_cap, n_dev, C, gamma, beta, mean, invstd, leak, train, dx, lddx, dgamma,
+                          dbeta, scratch, scratch_bytes, stream);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
+  k_bn_bwd_fused<<<G, L.threads, 2 * L.threads * sizeof(float), st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, part,
+                                                                      sync, gamma, beta, mean, invstd, leak, train,
+                                                                      dgamma, dbeta, dx, lddx);
+  count_launches(1);
+  B200_CHECK_LAUNCH("bn_bwd_sync");
   return 0;
 }

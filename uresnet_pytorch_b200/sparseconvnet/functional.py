@@ -259,7 +259,9 @@ class BatchNormAct(torch.autograd.Function):
     """Fused BatchNorm + leaky ReLU (leak = 0: ReLU, leak = 1: none)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, retention, leak, training, rows, n_dev):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, retention, leak, training, rows, n_dev,
+                sync=None, rows_hint=0):
+        """sync: the module's two-word barrier state (zeroed once) -> single-launch kernels for small inputs."""
         _check_cuda_f32(x, weight, bias)
         x = _rowmajor(x)
         C = x.shape[1]
@@ -270,10 +272,10 @@ class BatchNormAct(torch.autograd.Function):
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             mean = torch.empty(C, dtype=torch.float32, device=x.device)
             invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-            _lib.call("b200scn_bn_fwd_train", x.data_ptr(), x.stride(0), rows, n_dev, C, _lib.ptr(weight),
-                      _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), eps, retention, leak,
-                      y.data_ptr(), y.stride(0), mean.data_ptr(), invstd.data_ptr(), scratch.data_ptr(), nbytes,
-                      _stream())
+            _lib.call("b200scn_bn_fwd_train_sync", x.data_ptr(), x.stride(0), rows, n_dev, rows_hint, C,
+                      _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), eps, retention,
+                      leak, y.data_ptr(), y.stride(0), mean.data_ptr(), invstd.data_ptr(), _lib.ptr(sync),
+                      scratch.data_ptr(), nbytes, _stream())
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
@@ -281,13 +283,13 @@ class BatchNormAct(torch.autograd.Function):
                       _lib.ptr(bias), running_mean.data_ptr(), running_var.data_ptr(), eps, leak, y.data_ptr(),
                       y.stride(0), _stream())
         ctx.save_for_backward(x, weight, bias, mean, invstd)
-        ctx.misc = (leak, training, rows, n_dev)
+        ctx.misc = (leak, training, rows, n_dev, sync, rows_hint)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias, mean, invstd = ctx.saved_tensors
-        leak, training, rows, n_dev = ctx.misc
+        leak, training, rows, n_dev, sync, rows_hint = ctx.misc
         dy = _rowmajor(dy)
         C = x.shape[1]
         L = _lib.load()
@@ -296,12 +298,12 @@ class BatchNormAct(torch.autograd.Function):
         dx = torch.empty((rows, C), dtype=torch.float32, device=x.device)
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
-        _lib.call("b200scn_bn_bwd", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), rows, n_dev, C,
-                  _lib.ptr(weight), _lib.ptr(bias), mean.data_ptr(), invstd.data_ptr(), leak, int(training),
-                  dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(), nbytes,
-                  _stream())
+        _lib.call("b200scn_bn_bwd_sync", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), rows, n_dev,
+                  rows_hint, C, _lib.ptr(weight), _lib.ptr(bias), mean.data_ptr(), invstd.data_ptr(), leak,
+                  int(training), dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(sync),
+                  scratch.data_ptr(), nbytes, _stream())
         return (dx, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
-                None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 class InputGather(torch.autograd.Function):

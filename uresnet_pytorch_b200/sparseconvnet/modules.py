@@ -346,6 +346,7 @@ class BatchNormalization(torch.nn.Module):
             self.bias = torch.nn.Parameter(torch.zeros(nPlanes))
         else:
             self.weight = self.bias = None
+        self._sync = None
 
     def forward(self, x):
         if x.features.shape[1] != self.nPlanes:
@@ -353,9 +354,15 @@ class BatchNormalization(torch.nn.Module):
                                  % (self.nPlanes, x.features.shape[1]))
         md = x.metadata
         lv = md.level(x.spatial_size)
+        sync = self._sync
+        if sync is None or sync.device != x.features.device:
+            # barrier state of the single-launch kernels: owned by the module (never shared between calls that
+            # could overlap), zeroed once, not part of the state dict
+            sync = self._sync = torch.zeros(2, dtype=torch.int32, device=x.features.device)
+        hint = config.gpl_rows_by_size.get(tuple(x.spatial_size), 0) if md.static else 0
         out = F.BatchNormAct.apply(x.features, self.weight, self.bias, self.running_mean, self.running_var,
                                    float(self.eps), float(self.momentum), float(self.leakiness), self.training,
-                                   lv.rows, md.n_dev_ptr(lv))
+                                   lv.rows, md.n_dev_ptr(lv), sync, int(hint))
         return x._like(out)
 
     def input_spatial_size(self, out_size):
