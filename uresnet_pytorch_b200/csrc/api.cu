@@ -20,6 +20,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200SCN_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

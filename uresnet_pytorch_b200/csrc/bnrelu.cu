@@ -396,6 +396,7 @@ k_bn_fwd_fused(const float* __restrict__ x, int64_t ldx, int64_t n_cap, const in
                float leak, float* __restrict__ y, int64_t ldy, float* __restrict__ save_mean,
                float* __restrict__ save_invstd) {
   extern __shared__ float sm[];  // [3][threads]
+  pdl_wait();
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
@@ -501,6 +502,7 @@ k_bn_bwd_fused(const float* __restrict__ x, int64_t ldx, const float* __restrict
                const float* __restrict__ invstd, float leak, int train, float* __restrict__ dgamma,
                float* __restrict__ dbeta, float* __restrict__ dx, int64_t lddx) {
   extern __shared__ float sm[];  // [2][threads]
+  pdl_wait();
   const int n = live_rows(n_dev, n_cap);
   const int t = threadIdx.x, T = blockDim.x;
   const int c = t % C, rl = t / C;
@@ -741,9 +743,9 @@ extern "C" int b200scn_bn_fwd_train_sync(const float* x, int64_t ldx, int64_t n_
     return b200scn_bn_fwd_train(x, ldx, n_cap, n_dev, C, gamma, beta, running_mean, running_var, eps, retention, leak,
                                 y, ldy, save_mean, save_invstd, scratch, scratch_bytes, stream);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  k_bn_fwd_fused<<<G, L.threads, 3 * L.threads * sizeof(float), st>>>(x, ldx, n_cap, n_dev, C, L.RL, part, sync, gamma,
-                                                                      beta, running_mean, running_var, eps, retention,
-                                                                      leak, y, ldy, save_mean, save_invstd);
+  launch_pdl(k_bn_fwd_fused, dim3(G), dim3(L.threads), 3 * L.threads * sizeof(float), st, x, ldx, n_cap, n_dev, C, L.RL,
+             part, reinterpret_cast<unsigned int*>(sync), gamma, beta, running_mean, running_var, eps, retention, leak, y,
+             ldy, save_mean, save_invstd);
   count_launches(1);
   B200_CHECK_LAUNCH("bn_fwd_train_sync");
   return 0;
@@ -763,9 +765,9 @@ extern "C" int b200scn_bn_bwd_sync(const float* x, int64_t ldx, const float* dy,
     return b200scn_bn_bwd(x, ldx, dy, lddy, n_cap, n_dev, C, gamma, beta, mean, invstd, leak, train, dx, lddx, dgamma,
                           dbeta, scratch, scratch_bytes, stream);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
-  k_bn_bwd_fused<<<G, L.threads, 2 * L.threads * sizeof(float), st>>>(x, ldx, dy, lddy, n_cap, n_dev, C, L.RL, part,
-                                                                      sync, gamma, beta, mean, invstd, leak, train,
-                                                                      dgamma, dbeta, dx, lddx);
+  launch_pdl(k_bn_bwd_fused, dim3(G), dim3(L.threads), 2 * L.threads * sizeof(float), st, x, ldx, dy, lddy, n_cap, n_dev,
+             C, L.RL, part, reinterpret_cast<unsigned int*>(sync), gamma, beta, mean, invstd, leak, train, dgamma, dbeta,
+             dx, lddx);
   count_launches(1);
   B200_CHECK_LAUNCH("bn_bwd_sync");
   return 0;

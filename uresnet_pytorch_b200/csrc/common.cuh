@@ -41,6 +41,30 @@ void count_launches(int n);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: the grid may be scheduled while its stream predecessor drains (the launch
+// latency of the ~400 short kernels of a step overlaps the previous kernel's tail); every kernel launched
+// this way calls pdl_wait() before it touches global memory, and none triggers early, so a completed grid
+// still implies that everything before it in the stream completed.  B200SCN_PDL=0 turns it off.
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // live row count: min(*n_dev, n_cap) when a device count is given
 __device__ __forceinline__ int live_rows(const int32_t* n_dev, int64_t n_cap) {
   int n = (int)n_cap;

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
   constexpr bool WREG = WSMEM && (Q * MT <= 2);
   constexpr bool WLO = false;  // (no separate low-part copy: shared memory holds raw fp32, low parts are recomputed)
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
   const int split = p.split;
@@ -486,6 +487,7 @@ template <int MT, bool X3, int R, bool PACKED>
 __global__ void __launch_bounds__(512) k_conv_gpl_small(const GplParams p) {
   constexpr int CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
   const int n = live_rows(p.n_dev, p.n_cap);
   if ((int64_t)blockIdx.x * R >= n) return;
   const int warps = blockDim.x >> 5;
@@ -684,7 +686,7 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  k_conv_gpl<Q, MT, true, X3, 128><<<grid, warps * 32, fixed + warps * per_warp, st>>>(p);
+  launch_pdl(k_conv_gpl<Q, MT, true, X3, 128>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
@@ -724,7 +726,7 @@ int launch_small(GplParams p, int passes, cudaStream_t st) {
   if (gx > gmax) gx = gmax;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  k_conv_gpl_small<MT, X3, R, PACKED><<<grid, warps * 32, smem, st>>>(p);
+  launch_pdl(k_conv_gpl_small<MT, X3, R, PACKED>, grid, dim3(warps * 32), smem, st, p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl_small");
   return 0;

@@ -54,6 +54,7 @@ __host__ __device__ __forceinline__ int wgg_tiles_per_part(int n_tiles, int part
 template <int MT, int NT, bool X3>
 __global__ void __launch_bounds__(kWarps * 32) k_wgrad_gpl(const WgGplParams p) {
   extern __shared__ __align__(16) float red[];  // [16 MT][8 NT] cross-warp sum
+  pdl_wait();
   const int n = live_rows(p.n_dev, p.n_cap);
   const int R = p.tile_rows, K = p.K;
   const int n_tiles = (n + R - 1) / R;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_wgrad_gpl(const WgGplParams p) 
 __global__ void k_wgrad_gpl_fold(const float* __restrict__ part, int K, int extra, int centre, int64_t cc, int parts,
                                  int tile_rows, int64_t n_cap, const int32_t* __restrict__ n_dev, float* __restrict__ dW,
                                  int accumulate) {
+  pdl_wait();
   const int n = live_rows(n_dev, n_cap);
   const int n_tiles = (n + tile_rows - 1) / tile_rows;
   const int tpp = wgg_tiles_per_part(n_tiles, parts);
@@ -277,7 +279,7 @@ WggPlan wgg_plan(int K, int Ca, int Cb, int64_t n_cap, int64_t n_expect, int til
 template <int MT, int NT, bool X3>
 int wgg_launch(const WgGplParams& p, const WggPlan& pl, cudaStream_t st) {
   dim3 grid((unsigned)(p.K + p.extra), (unsigned)pl.parts, (unsigned)(pl.ca_chunks * pl.cb_chunks));
-  k_wgrad_gpl<MT, NT, X3><<<grid, kWarps * 32, (size_t)16 * MT * 8 * NT * 4, st>>>(p);
+  launch_pdl(k_wgrad_gpl<MT, NT, X3>, grid, dim3(kWarps * 32), (size_t)16 * MT * 8 * NT * 4, st, p);
   return 0;
 }
 
@@ -332,8 +334,8 @@ extern "C" int b200scn_wgrad_gpl(const float* A, int64_t lda, const float* B, in
   if (rc) return rc;
   int64_t gsz = cdiv((int64_t)K * cc, 256);
   if (gsz > 1024) gsz = 1024;
-  k_wgrad_gpl_fold<<<(int)gsz, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), K, pl.extra, pl.centre, cc, pl.parts,
-                                            tile_rows, n_cap, n_dev, dW, accumulate);
+  launch_pdl(k_wgrad_gpl_fold, dim3((unsigned)gsz), dim3(256), 0, st, reinterpret_cast<const float*>(scratch), K,
+             pl.extra, pl.centre, cc, pl.parts, tile_rows, n_cap, n_dev, dW, accumulate);
   count_launches(2);
   B200_CHECK_LAUNCH("wgrad_gpl");
   return 0;
