@@ -13,8 +13,9 @@
 // `full` mbarrier after cp.async.wait_group + fence.proxy.async; the MMA thread waits on it, issues 4 MMAs
 // (K = 8 each), and tcgen05.commit releases the stage (`empty`) -- or, after the last block, hands the
 // accumulator to the epilogue: tcgen05.ld 32x32b, + bias, 16-byte stores.
-// Single-pass TF32 (10-bit mantissa operands, fp32 accumulate): B200SCN_MATH_TF32 only; the exact-fp32 FFMA
-// path (csrc/dense.cu) stays the default of the dense modules.
+// Math modes: B200SCN_MATH_TF32 = single pass (10-bit mantissa operands, fp32 accumulate); B200SCN_MATH_TF32X3 =
+// 3-term split (fp32-equivalent, see k_dense_conv_tc<true>); B200SCN_MATH_FP32 keeps the exact FFMA path
+// (csrc/dense.cu), which also serves channel counts this kernel does not take.
 #include "common.cuh"
 
 namespace b200scn {
