@@ -484,7 +484,7 @@ struct GplChunk {
 };
 
 template <int MT, bool X3, int R, bool PACKED>
-__global__ void __launch_bounds__(512) k_conv_gpl_small(const GplParams p) {
+__global__ void __launch_bounds__(512, MT == 1 ? 2 : 1) k_conv_gpl_small(const GplParams p) {
   constexpr int CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_wait();
