@@ -246,7 +246,7 @@ int b200scn_dense_conv(const float* in, int64_t ldi, const float* W, int64_t w_s
                        int64_t ldo, void* stream);
 /* the same convolution on the tcgen05 tensor cores (implicit GEMM, kind::tf32, accumulators in TMEM;
  * csrc/dense_tc.cu), fp32 accumulate; math_mode B200SCN_MATH_TF32 (single pass) or B200SCN_MATH_TF32X3
- * (3-term split, fp32-equivalent).  Needs Cin % 32 == 0 and Cout % 16 == 0, else returns
+ * (3-term split, fp32-equivalent).  Needs Cin % 32 == 0 or Cin == 16, and Cout % 16 == 0, else returns
  * B200SCN_ERR_UNSUPPORTED and the caller uses b200scn_dense_conv. */
 int64_t b200scn_dense_conv_tc_scratch_bytes(int taps, int Cin, int Cout);
 int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si, int64_t w_so,
@@ -254,8 +254,10 @@ int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* W, int64_t 
                           int64_t ldo, int math_mode, void* scratch, int64_t scratch_bytes, void* stream);
 int64_t b200scn_dense_wgrad_scratch_bytes(const int32_t* geom_host, int batch, int Ca, int Cb);
 /* dW[k][ca][cb] = sum_o A[idx(o,k)][ca] * B[o][cb] (gather_b == 0) or A[o][ca] * B[idx(o,k)][cb] (gather_b == 1) */
+/* math_mode != B200SCN_MATH_FP32 and channel counts that are multiples of 16: tensor-core kernel (csrc/wgrad_mma.cu) */
 int b200scn_dense_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* geom_host, int batch,
-                        int gather_b, int Ca, int Cb, float* dW, void* scratch, int64_t scratch_bytes, void* stream);
+                        int gather_b, int Ca, int Cb, float* dW, int math_mode, void* scratch, int64_t scratch_bytes,
+                        void* stream);
 /* F.pad(mode='replicate') on channels-last data and its backward; sizes are (z, y, x) host int32[3] */
 int b200scn_pad_replicate(const float* src, float* dst, int batch, int C, const int32_t* in_sz_host,
                           const int32_t* pl_host, const int32_t* pr_host, int backward, void* stream);

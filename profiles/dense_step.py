@@ -22,6 +22,7 @@ ap.add_argument("--ss", type=int, default=192)
 ap.add_argument("--bs", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--math", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
+ap.add_argument("--profile", action="store_true", help="per-kernel device time of one step (torch.profiler)")
 a = ap.parse_args()
 mode = {"fp32": scn.MATH_FP32, "tf32x3": scn.MATH_TF32X3, "tf32": scn.MATH_TF32}[a.math]
 dev = torch.device("cuda")
@@ -62,6 +63,23 @@ for _ in range(a.steps):
     e1.synchronize()
     times.append(e0.elapsed_time(e1))
 ms = sum(times) / len(times)
+if a.profile:
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = re.sub(r"^void ", "", ev.name)
+            name = re.sub(r"(b200scn::|\(anonymous namespace\)::)", "", name)[:70]
+            agg[name][0] += 1
+            agg[name][1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+    tot = sum(v[1] for v in agg.values())
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
+        print("%-70s n=%4d  ms=%9.2f  %5.1f%%" % (k, c, t / 1e3, 100 * t / tot))
 print(json.dumps({"config": "uresnet_dense 3D train ss=%d uns=5 uf=16 nc=5 bs=%d" % (a.ss, a.bs), "math": a.math,
                   "ms_per_step": ms, "grid_voxels_per_s": a.bs * a.ss ** 3 / ms * 1e3, "loss": float(loss),
                   "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "steps": a.steps}))

@@ -129,7 +129,8 @@ def test_dense_batchnorm_matches_torch():
 
 @pytest.mark.parametrize("kind,dims,k,stride,cin,cout", [
     ("conv", 3, 3, 1, 32, 32), ("conv", 3, 3, 2, 64, 48), ("conv", 2, 3, 1, 32, 16), ("conv", 3, 1, 2, 96, 32),
-    ("convT", 3, 3, 2, 64, 32), ("conv", 3, 3, 1, 32, 272)])
+    ("convT", 3, 3, 2, 64, 32), ("conv", 3, 3, 1, 32, 272), ("conv", 3, 3, 1, 16, 16), ("conv", 3, 3, 2, 16, 32),
+    ("convT", 3, 3, 2, 32, 16), ("conv", 2, 3, 1, 16, 48)])
 def test_dense_conv_tcgen05_matches_ffma(kind, dims, k, stride, cin, cout):
     """csrc/dense_tc.cu (tcgen05.mma kind::tf32, TMEM accumulators, implicit-GEMM gather) against the exact-fp32
     FFMA kernel on the same module: forward and input gradient, single-pass TF32 tolerance."""
@@ -142,15 +143,20 @@ def test_dense_conv_tcgen05_matches_ffma(kind, dims, k, stride, cin, cout):
     mod = (Conv(dims, cin, cout, k, stride) if kind == "conv" else ConvTranspose(dims, cin, cout)).cuda()
     shape = (2,) + ((size,) * 3 if dims == 3 else (1, size, size)) + (cin,)
     x0 = torch.randn(shape, device="cuda")
-    outs, grads = [], []
+    outs, grads, wgrads = [], [], []
     for mode in (scn.MATH_FP32, scn.MATH_TF32, scn.MATH_TF32X3):
         x = x0.clone().requires_grad_(True)
+        mod.zero_grad(set_to_none=True)
         with scn.math(mode):
             y = mod(x)
             (y * torch.linspace(-1, 1, y.numel(), device="cuda").reshape(y.shape)).sum().backward()
         torch.cuda.synchronize()
         outs.append(y.detach())
         grads.append(x.grad.detach())
+        wgrads.append([p.grad.detach().clone() for p in mod.parameters()])
+    # weight gradients: the tensor-core modes run csrc/wgrad_mma.cu over the implicit (voxel, tap) rule
+    for a, b, c in zip(*wgrads):
+        assert rel_l2(b, a) <= 2e-3 and rel_l2(c, a) <= 1e-5, (rel_l2(b, a), rel_l2(c, a))
     assert outs[0].shape == outs[1].shape == outs[2].shape
     assert (outs[0] - outs[1]).abs().max().item() <= 5e-3 * outs[0].abs().max().item()
     assert (grads[0] - grads[1]).abs().max().item() <= 5e-3 * grads[0].abs().max().item()

@@ -229,3 +229,34 @@ def test_fused_adam_matches_torch_adam():
     pb[1].grad = None
     mine.step()
     assert torch.equal(pb[1], before) and int(mine.step_dev.item()) == 7
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    """save_state / load_state use the reference's checkpoint layout (R/uresnet/trainval.py:32-40, 171-196):
+    'module.'-prefixed state dict + torch.optim.Adam-format optimizer state; a restored trainer (eager or
+    captured graph) continues bit-identically, and torch.optim.Adam accepts the optimizer state."""
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    blobs = [event_blob(2, 32, seed=s) for s in (1, 2, 3, 4)]
+    cap = max(len(b[0]) for b in blobs) + 5
+    a = Trainer(flags, lr=1e-3, graph=False, events_per_step=2, seed=5)
+    for data, label in blobs[:2]:
+        a.train_step(data, label)
+    path = str(tmp_path / "weights-1.ckpt")
+    a.save_state(path, 1)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"global_step", "state_dict", "optimizer"} and ck["global_step"] == 1
+    assert all(k.startswith("module.") for k in ck["state_dict"])
+    assert "module.sparseModel.1.weight" in ck["state_dict"] and "module.linear.bias" in ck["state_dict"]
+    ref_opt = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in a.net.parameters()], lr=1e-3)
+    ref_opt.load_state_dict(ck["optimizer"])  # torch's own loader validates the layout
+    assert int(ref_opt.state_dict()["state"][0]["step"]) == 2
+    nxt = [a.train_step(d, l)["loss"] for d, l in blobs[2:]]
+    for graph in (False, True):
+        b = Trainer(flags, lr=1e-3, graph=graph, capacity=cap if graph else None, events_per_step=2, seed=99)
+        if graph:
+            b.train_step(*blobs[0])  # capture first: restoring must work on a live graph
+        assert b.load_state(path) == 2
+        got = [b.train_step(d, l)["loss"] for d, l in blobs[2:]]
+        for x, y in zip(got, nxt):
+            assert abs(x - y) <= (2e-4 if graph else 1e-6) * abs(y), (graph, got, nxt)

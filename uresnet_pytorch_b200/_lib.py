@@ -62,7 +62,7 @@ SIGNATURES = {
     "b200scn_add_rows": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_dense_conv": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "b200scn_dense_wgrad_scratch_bytes": (_I64, [_P, _I32, _I32, _I32]),
-    "b200scn_dense_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P]),
+    "b200scn_dense_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I64, _P]),
     "b200scn_pad_replicate": (_I32, [_P, _P, _I32, _I32, _P, _P, _P, _I32, _P]),
     "b200scn_colsum_scratch_bytes": (_I64, [_I32]),
     "b200scn_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _I64, _P]),

@@ -75,7 +75,7 @@ static int conv_impl() {
 bool wgrad_mma_supported(int64_t, int, int, int, int64_t, int64_t, const void*, const void*);
 int64_t wgrad_scratch_bytes_mma(int64_t, int, int, int);
 int wgrad_table_mma(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
-                    const int32_t*, int, int, float*, int, int, void*, int64_t, cudaStream_t);
+                    const int32_t*, int, int, float*, int, int, void*, int64_t, cudaStream_t, const DenseGeom*);
 
 }  // namespace b200scn
 
@@ -147,7 +147,7 @@ extern "C" int b200scn_wgrad_table(const float* A, int64_t lda, const float* B, 
   B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "wgrad_table: bad math mode %d", math_mode);
   if (math_mode != B200SCN_MATH_FP32 && wgrad_mma_supported(n_cap, K, Ca, Cb, lda, ldb, A, B))
     return wgrad_table_mma(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, math_mode,
-                           scratch, scratch_bytes, (cudaStream_t)stream);
+                           scratch, scratch_bytes, (cudaStream_t)stream, nullptr);
   return wgrad_table_simt(A, lda, B, ldb, table, ld, K, gather_b, n_cap, n_dev, Ca, Cb, dW, accumulate, scratch,
                           scratch_bytes, (cudaStream_t)stream, DenseGeom{});
 }

@@ -10,11 +10,16 @@
 //   wgrad (both)        dW[k]  = sum_o in[idx(o,k)]^T dout[o]
 // The reference pads with F.pad(mode='replicate') before zero-padding-free convolutions
 // (uresnet_dense.py:19-26,75-80); pad_replicate_{fwd,bwd} below do the same explicitly.
-// This first version is the exact-fp32 FFMA path; the tcgen05 implicit-GEMM kernel for the
-// C_in >= 128 levels is the next step.
+// This file is the exact-fp32 FFMA path and the entry points; the tensor-core math modes route forward / dgrad
+// to the tcgen05 implicit-GEMM kernel (csrc/dense_tc.cu) and wgrad to csrc/wgrad_mma.cu.
 #include "common.cuh"
 
 namespace b200scn {
+
+bool wgrad_mma_supported(int64_t, int, int, int, int64_t, int64_t, const void*, const void*);
+int64_t wgrad_scratch_bytes_mma(int64_t, int, int, int);
+int wgrad_table_mma(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
+                    const int32_t*, int, int, float*, int, int, void*, int64_t, cudaStream_t, const DenseGeom*);
 
 int conv_dense_simt(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, int64_t, int, int, float*,
                     int64_t, const DenseGeom&, const float*, cudaStream_t);
@@ -75,16 +80,40 @@ __global__ void k_pad_bwd(const float* __restrict__ dout, float* __restrict__ di
   }
 }
 
-// column sums of an [n, C] matrix (bias gradients): per-CTA partials + ordered fold by the last CTA
-__global__ void k_colsum(const float* __restrict__ x, int64_t ldx, int64_t n, int C, float* __restrict__ part,
-                         unsigned int* counter, float* __restrict__ out) {
+// column sums of an [n, C] matrix (bias gradients): per-CTA partials + ordered fold by the last CTA.
+// thread = (column c, row lane rl): consecutive threads read consecutive columns of a row (coalesced for any C);
+// the row lanes of a column are summed in lane order, the CTA partials in CTA order (deterministic).
+constexpr int kColsumThreads = 256;
+__global__ void __launch_bounds__(kColsumThreads) k_colsum(const float* __restrict__ x, int64_t ldx, int64_t n, int C,
+                                                           float* __restrict__ part, unsigned int* counter,
+                                                           float* __restrict__ out) {
   __shared__ bool is_last;
+  __shared__ float sm[kColsumThreads];
   const int64_t rpb = (n + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = blockIdx.x * rpb, r1 = r0 + rpb < n ? r0 + rpb : n;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += __ldg(x + r * ldx + c);
-    part[(int64_t)blockIdx.x * C + c] = s;
+  const int t = threadIdx.x;
+  const int CW = C < kColsumThreads ? C : kColsumThreads;  // columns handled per sweep
+  const int RL = kColsumThreads / CW;
+  const int cl = t % CW, rl = t / CW;
+  for (int c0 = 0; c0 < C; c0 += CW) {
+    const int c = c0 + cl;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rl < RL && c < C) {
+      int64_t r = r0 + rl;
+      for (; r + 3 * RL < r1; r += 4 * RL) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += __ldg(x + (r + u * RL) * ldx + c);
+      }
+      for (; r < r1; r += RL) s[0] += __ldg(x + r * ldx + c);
+    }
+    __syncthreads();
+    sm[t] = (s[0] + s[1]) + (s[2] + s[3]);
+    __syncthreads();
+    if (rl == 0 && c < C) {
+      float a = sm[cl];
+      for (int q = 1; q < RL; ++q) a += sm[q * CW + cl];
+      part[(int64_t)blockIdx.x * C + c] = a;
+    }
   }
   __threadfence();
   __syncthreads();
@@ -93,9 +122,9 @@ __global__ void k_colsum(const float* __restrict__ x, int64_t ldx, int64_t n, in
   if (!is_last) return;
   __threadfence();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(part + (int64_t)b * C + c);
-    out[c] = s;
+    float a = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(part + (int64_t)b * C + c);
+    out[c] = a;
   }
   if (threadIdx.x == 0) *counter = 0u;
 }
@@ -145,17 +174,24 @@ extern "C" int b200scn_dense_conv(const float* in, int64_t ldi, const float* W, 
 extern "C" int64_t b200scn_dense_wgrad_scratch_bytes(const int32_t* geom_host, int batch, int Ca, int Cb) {
   DenseGeom g;
   if (read_geom(geom_host, &g)) return -1;
-  return wgrad_scratch_bytes_simt(out_rows(g, batch), taps(g), Ca, Cb);
+  const int64_t a = wgrad_scratch_bytes_simt(out_rows(g, batch), taps(g), Ca, Cb);
+  const int64_t b = wgrad_scratch_bytes_mma(out_rows(g, batch), taps(g), Ca, Cb);
+  return a > b ? a : b;
 }
 
-/* dW[k][ca][cb] = sum_o A[idx(o,k)][ca] * B[o][cb]  (gather_b == 0)   or   A[o][ca] * B[idx(o,k)][cb]  (gather_b == 1) */
+/* dW[k][ca][cb] = sum_o A[idx(o,k)][ca] * B[o][cb]  (gather_b == 0)   or   A[o][ca] * B[idx(o,k)][cb]  (gather_b == 1).
+ * math_mode != B200SCN_MATH_FP32 and 16-multiple channel counts: the tensor-core kernel of the sparse path
+ * (csrc/wgrad_mma.cu) with the rule of (voxel, tap) computed from the geometry instead of read from a table. */
 extern "C" int b200scn_dense_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* geom_host,
-                                   int batch, int gather_b, int Ca, int Cb, float* dW, void* scratch,
+                                   int batch, int gather_b, int Ca, int Cb, float* dW, int math_mode, void* scratch,
                                    int64_t scratch_bytes, void* stream) {
   DenseGeom g;
   if (int rc = read_geom(geom_host, &g)) return rc;
   const int64_t n = out_rows(g, batch);
   B200_CHECK_ARG(n < (1ll << 31), "dense_wgrad: too many voxels");
+  if (math_mode != B200SCN_MATH_FP32 && taps(g) <= 64 && wgrad_mma_supported(n, taps(g), Ca, Cb, lda, ldb, A, B))
+    return wgrad_table_mma(A, lda, B, ldb, nullptr, 0, taps(g), gather_b, n, nullptr, Ca, Cb, dW, 0, math_mode, scratch,
+                           scratch_bytes, (cudaStream_t)stream, &g);
   return wgrad_table_simt(A, lda, B, ldb, nullptr, 0, taps(g), gather_b, n, nullptr, Ca, Cb, dW, 0, scratch,
                           scratch_bytes, (cudaStream_t)stream, g);
 }
@@ -202,7 +238,7 @@ extern "C" int b200scn_colsum(const float* x, int64_t ldx, int64_t n, int C, flo
   const int64_t cap = (int64_t)sm_count() * 2;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  k_colsum<<<(int)grid, 128, 0, st>>>(x, ldx, n, C, part, counter, out);
+  k_colsum<<<(int)grid, kColsumThreads, 0, st>>>(x, ldx, n, C, part, counter, out);
   count_launches(1);
   B200_CHECK_LAUNCH("colsum");
   return 0;

@@ -71,19 +71,27 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Wt[tap][chunk][co][32] = W[tap][32 chunk + j][co]   (K-major copy: 128 contiguous bytes per (co, chunk))
+// K blocks: the contraction axis is the flattened (tap, ci) index, walked 32 at a time.  Cin % 32 == 0: block kb =
+// (tap, 32-channel chunk).  Cin == 16: block kb = the 16 channels of taps 2 kb and 2 kb + 1 (the odd last tap is
+// paired with zeros), so the 16-channel level runs on the same 128-byte swizzle rows.
+__host__ __device__ __forceinline__ int dtc_blocks(int taps, int Cin) {
+  return Cin == 16 ? (taps + 1) / 2 : taps * (Cin / kBK);
+}
+
+// Wt[kb][co][32] = W[tap(kb, j)][ci(kb, j)][co]   (K-major copy: 128 contiguous bytes per (co, block))
 __global__ void k_dense_pack_wt(const float* __restrict__ W, int64_t w_sk, int64_t w_si, int64_t w_so, int taps, int Cin,
                                 int Cout, float* __restrict__ Wt, float* __restrict__ Wt_lo) {
-  const int64_t total = (int64_t)taps * Cin * Cout;
+  const int64_t total = (int64_t)dtc_blocks(taps, Cin) * kBK * Cout;
   const int chunks = Cin / kBK;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(e % kBK);
     int64_t rest = e / kBK;
     const int co = (int)(rest % Cout);
-    rest /= Cout;
-    const int chunk = (int)(rest % chunks);
-    const int tap = (int)(rest / chunks);
-    const float v = __ldg(W + tap * w_sk + (int64_t)(chunk * kBK + j) * w_si + co * w_so);
+    const int kb = (int)(rest / Cout);
+    int tap, ci;
+    if (Cin == 16) { tap = 2 * kb + (j >> 4); ci = j & 15; }
+    else { tap = kb / chunks; ci = (kb - tap * chunks) * kBK + j; }
+    const float v = tap < taps ? __ldg(W + tap * w_sk + (int64_t)ci * w_si + co * w_so) : 0.f;
     if (Wt_lo != nullptr) {  // 3xTF32: high part = truncation to tf32, low part = exact remainder
       const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       Wt[e] = hi;
@@ -96,7 +104,7 @@ __global__ void k_dense_pack_wt(const float* __restrict__ W, int64_t w_sk, int64
 
 struct DtcParams {
   const float* in; int64_t ldi;
-  const float* Wt;      // packed weights, [taps][Cin/32][Cout][32]
+  const float* Wt;      // packed weights, [K blocks][Cout][32]
   const float* Wt_lo;   // low parts (3xTF32) or NULL
   const float* bias;
   float* out; int64_t ldo;
@@ -124,8 +132,9 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
   const uint32_t a_lo_off = a_bytes, b_off = a_bytes * (X3 ? 2 : 1), b_lo_off = b_off + b_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int co0 = blockIdx.y * N;
-  const int chunks = p.Cin / kBK;
-  const int n_kb = p.taps * chunks;
+  const int chunks = p.Cin / kBK;  // (0 in the two-taps-per-block mode of Cin == 16)
+  const bool half = p.Cin == 16;
+  const int n_kb = dtc_blocks(p.taps, p.Cin);
   const int64_t o0 = (int64_t)blockIdx.x * kBM;
 
   if (tid == 0) {
@@ -148,17 +157,26 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
     const int64_t o = o0 + r;
     const uint32_t sw = (uint32_t)(r & 7);
     int cur_tap = -1, idx = -1;
-    auto row_of = [&](int kb) -> const float* {  // input row of block kb (nullptr: zero row)
+    // the two 16-channel halves of this voxel's row of block kb (nullptr: zeros)
+    auto rows_of = [&](int kb, const float*& ra, const float*& rb) {
+      if (half) {
+        const int t0 = 2 * kb, t1 = t0 + 1;
+        const int i0 = o < p.n_out ? dense_index(p.geom, (int)o, t0) : -1;
+        const int i1 = (o < p.n_out && t1 < p.taps) ? dense_index(p.geom, (int)o, t1) : -1;
+        ra = i0 >= 0 ? p.in + (int64_t)i0 * p.ldi : nullptr;
+        rb = i1 >= 0 ? p.in + (int64_t)i1 * p.ldi : nullptr;
+        return;
+      }
       const int tap = kb / chunks, chunk = kb - tap * chunks;
       if (tap != cur_tap) {
         cur_tap = tap;
         idx = o < p.n_out ? dense_index(p.geom, (int)o, tap) : -1;
       }
-      return idx >= 0 ? p.in + (int64_t)idx * p.ldi + chunk * kBK : nullptr;
+      ra = idx >= 0 ? p.in + (int64_t)idx * p.ldi + chunk * kBK : nullptr;
+      rb = ra ? ra + 16 : nullptr;
     };
     auto copy_b = [&](int kb, int s) {
-      const int tap = kb / chunks, chunk = kb - tap * chunks;
-      const int64_t woff = ((int64_t)(tap * chunks + chunk) * p.Cout + co0) * kBK;
+      const int64_t woff = ((int64_t)kb * p.Cout + co0) * kBK;
       for (int n = r; n < N; n += kProducers) {
         const uint32_t b_dst = smem_u32(smem + (size_t)s * stage_bytes + b_off) + (uint32_t)n * 128;
         const uint32_t swn = (uint32_t)(n & 7);
@@ -176,12 +194,13 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
         if (kb < n_kb) {
           const int s = kb % kStages;
           mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
-          const float* a_row = row_of(kb);
+          const float *ra, *rb;
+          rows_of(kb, ra, rb);
           const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)r * 128;
-          const float* a_src = a_row ? a_row : p.in;
-          const int nbytes = a_row ? 16 : 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp_async16_zfill(a_dst + ((j ^ sw) << 4), a_src + 4 * j, nbytes);
+          for (int j = 0; j < 4; ++j) cp_async16_zfill(a_dst + ((j ^ sw) << 4), (ra ? ra : p.in) + 4 * j, ra ? 16 : 0);
+#pragma unroll
+          for (int j = 4; j < 8; ++j) cp_async16_zfill(a_dst + ((j ^ sw) << 4), (rb ? rb : p.in) + 4 * (j - 4), rb ? 16 : 0);
           copy_b(kb, s);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -194,15 +213,19 @@ __global__ void __launch_bounds__(kProducers + 32, 1) k_dense_conv_tc(const DtcP
       }
     } else {
       float4 cur[8], nxt[8];
-      auto load_row = [&](const float* a_row, float4 (&v)[8]) {
+      auto load_row = [&](int kb, float4 (&v)[8]) {
+        const float *ra, *rb;
+        rows_of(kb, ra, rb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          v[j] = a_row ? __ldg(reinterpret_cast<const float4*>(a_row) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) {
+          v[j] = ra ? __ldg(reinterpret_cast<const float4*>(ra) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 + j] = rb ? __ldg(reinterpret_cast<const float4*>(rb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       };
-      load_row(row_of(0), cur);
+      load_row(0, cur);
       for (int kb = 0; kb < n_kb; ++kb) {
         const int s = kb % kStages;
-        if (kb + 1 < n_kb) load_row(row_of(kb + 1), nxt);  // in flight while this block is split and stored
+        if (kb + 1 < n_kb) load_row(kb + 1, nxt);  // in flight while this block is split and stored
         mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);
         copy_b(kb, s);
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -294,10 +317,10 @@ int read_geom_public(const int32_t* g, DenseGeom* out);
 using namespace b200scn;
 
 extern "C" int64_t b200scn_dense_conv_tc_scratch_bytes(int taps, int Cin, int Cout) {
-  return (int64_t)2 * taps * Cin * Cout * 4 + 512;
+  return (int64_t)2 * dtc_blocks(taps, Cin) * kBK * Cout * 4 + 512;
 }
 
-/* tcgen05 implicit-GEMM variant of b200scn_dense_conv (single-pass TF32).  Needs Cin % 32 == 0, Cout % 16 == 0;
+/* tcgen05 implicit-GEMM variant of b200scn_dense_conv.  Needs Cin % 32 == 0 or Cin == 16, and Cout % 16 == 0;
  * returns B200SCN_ERR_UNSUPPORTED otherwise (the caller falls back to b200scn_dense_conv). */
 extern "C" int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* W, int64_t w_sk, int64_t w_si,
                                      int64_t w_so, const float* bias, const int32_t* geom_host, int batch, int Cin,
@@ -306,8 +329,8 @@ extern "C" int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   DenseGeom g;
   if (int rc = read_geom_public(geom_host, &g)) return rc;
-  if (Cin % 32 != 0 || Cout % 16 != 0 || Cin < 32 || Cout < 16) {
-    set_error("dense_conv_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
+  if ((Cin % 32 != 0 && Cin != 16) || Cout % 16 != 0 || Cin < 16 || Cout < 16) {
+    set_error("dense_conv_tc: needs Cin %% 32 == 0 or Cin == 16, and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
     return B200SCN_ERR_UNSUPPORTED;
   }
   B200_CHECK_ARG(ldi % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "dense_conv_tc: input rows must be 16-byte aligned");
@@ -317,7 +340,7 @@ extern "C" int b200scn_dense_conv_tc(const float* in, int64_t ldi, const float* 
   B200_CHECK_ARG(n < (1ll << 31) && n >= 1, "dense_conv_tc: bad voxel count");
   B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "dense_conv_tc: tensor-core math modes only");
   const bool x3 = math_mode == B200SCN_MATH_TF32X3;
-  const int64_t total = (int64_t)taps * Cin * Cout;
+  const int64_t total = (int64_t)dtc_blocks(taps, Cin) * kBK * Cout;
   float* Wt = reinterpret_cast<float*>(scratch);
   float* Wt_lo = x3 ? Wt + ((total + 63) / 64) * 64 : nullptr;
   {

@@ -37,6 +37,7 @@ struct WgParams {
   float* part;
   int x3;
   float* dW; int accumulate; int fused_fold;
+  int use_geom; DenseGeom geom;  // dense path: the rule of (row, offset) is computed, not looked up
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kWarpsMax * 32) k_wgrad_mma(const WgParams p) 
   for (int c0 = r_begin; c0 < r_end; c0 += nthr) {
     const int r = c0 + tid;
     int e = -1;
-    if (r < r_end) e = p.table ? __ldg(p.table + (int64_t)k * p.ld + r) : r;
+    if (r < r_end) e = p.use_geom ? dense_index(p.geom, r, k) : (p.table ? __ldg(p.table + (int64_t)k * p.ld + r) : r);
     const uint32_t m = __ballot_sync(0xffffffffu, e >= 0);
     if (lane == 0) wsum[warp] = __popc(m);
     __syncthreads();
@@ -339,7 +340,7 @@ int64_t wgrad_scratch_bytes_mma(int64_t n_cap, int K, int Ca, int Cb) {
 
 int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, const int32_t* table, int64_t ld, int K,
                     int gather_b, int64_t n_cap, const int32_t* n_dev, int Ca, int Cb, float* dW, int accumulate,
-                    int math_mode, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
+                    int math_mode, void* scratch, int64_t scratch_bytes, cudaStream_t st, const DenseGeom* geom) {
   const int64_t elems = (int64_t)K * Ca * Cb;
   if (n_cap == 0) {
     if (!accumulate) B200_CUDA(cudaMemsetAsync(dW, 0, (size_t)elems * 4, st));
@@ -360,6 +361,8 @@ int wgrad_table_mma(const float* A, int64_t lda, const float* B, int64_t ldb, co
     fused = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   p.dW = dW; p.accumulate = accumulate; p.fused_fold = fused;
+  p.use_geom = geom != nullptr ? 1 : 0;
+  if (geom != nullptr) p.geom = *geom; else p.geom = DenseGeom{};
   B200_CHECK_ARG(K <= 64 && pl.zsplits <= 8, "wgrad_mma: K > 64 or more than 8 column splits");
   int rc = 0;
   switch (pl.tpw) {

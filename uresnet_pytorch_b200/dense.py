@@ -72,7 +72,7 @@ def _conv_call(x_ptr, Cin, w_ptr, w_si, w_so, bias, g, B, Cout, out, T, device):
     math modes (tf32x3 = fp32-equivalent, tf32 = single pass) when the channel counts allow, else the
     exact-fp32 FFMA kernel."""
     from .sparseconvnet import config
-    if config.math_mode != config.MATH_FP32 and Cin % 32 == 0 and Cout % 16 == 0:
+    if config.math_mode != config.MATH_FP32 and (Cin % 32 == 0 or Cin == 16) and Cout % 16 == 0:
         L = _lib.load()
         nbytes = L.b200scn_dense_conv_tc_scratch_bytes(T, Cin, Cout)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -133,8 +133,9 @@ class _DenseConv(torch.autograd.Function):
             nbytes = L.b200scn_dense_wgrad_scratch_bytes(g, B, Cin, Cout)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             dwk = torch.empty((T, Cin, Cout), dtype=torch.float32, device=x.device)
+            from .sparseconvnet import config
             _lib.call("b200scn_dense_wgrad", x.data_ptr(), Cin, dout.data_ptr(), Cout, g, B, 0, Cin, Cout,
-                      dwk.data_ptr(), scratch.data_ptr(), nbytes, _stream())
+                      dwk.data_ptr(), config.math_mode, scratch.data_ptr(), nbytes, _stream())
             dw = (dwk.permute(1, 2, 0) if transposed else dwk.permute(2, 1, 0)).reshape(w_shape).contiguous()
         if has_bias and ctx.needs_input_grad[2]:
             nb = L.b200scn_colsum_scratch_bytes(Cout)

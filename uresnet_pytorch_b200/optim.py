@@ -64,3 +64,45 @@ class FusedAdam(object):
         self._keep = host
         _lib.call("b200scn_adam_step", jobs.data_ptr(), n, self._max, self.step_dev.data_ptr(), self.ticket.data_ptr(),
                   self.lr, self.betas[0], self.betas[1], self.eps, torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------------------------
+    def state_dict(self):
+        """torch.optim.Adam's state-dict layout (what the reference stores under 'optimizer',
+        /root/reference/uresnet/trainval.py:32-40), so checkpoints move both ways."""
+        step = self.step_dev.to(torch.float32).reshape(()).cpu()
+        state = {i: {"step": step.clone(), "exp_avg": self.exp_avg[i].detach().clone(),
+                     "exp_avg_sq": self.exp_avg_sq[i].detach().clone()} for i in range(len(self.params))}
+        if int(step.item()) == 0:
+            state = {}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        groups = sd.get("param_groups", [])
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError("FusedAdam.load_state_dict: %d parameters in the checkpoint, %d here"
+                             % (len(order), len(self.params)))
+        if groups:
+            g = groups[0]
+            if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False):
+                raise ValueError("FusedAdam: weight_decay / amsgrad checkpoints are not supported")
+            self.lr, self.eps = float(g["lr"]), float(g["eps"])
+            self.betas = (float(g["betas"][0]), float(g["betas"][1]))
+        steps = set()
+        for pos, key in enumerate(order):
+            st = sd["state"].get(key)
+            if st is None:
+                self.exp_avg[pos].zero_()
+                self.exp_avg_sq[pos].zero_()
+                continue
+            self.exp_avg[pos].copy_(st["exp_avg"])
+            self.exp_avg_sq[pos].copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam keeps one step counter; the checkpoint holds %s" % sorted(steps))
+        self.step_dev.fill_(steps.pop() if steps else 0)
+

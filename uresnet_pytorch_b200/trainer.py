@@ -276,6 +276,41 @@ class Trainer(object):
             vals = out.tolist()
         return {"loss": vals[0], "acc": vals[1]}
 
+    # ------------------------------------------------------------------------------------
+    def save_state(self, path, iteration):
+        """The reference's checkpoint (R/uresnet/trainval.py:32-40): {'global_step', 'state_dict', 'optimizer'};
+        state-dict keys carry the 'module.' prefix of the DataParallel wrapper the reference saves through
+        (R/uresnet/trainval.py:159-163), so its tools read these files and vice versa."""
+        torch.cuda.synchronize(self.device)
+        sd = {"module." + k: v.detach().clone() for k, v in self.net.state_dict().items()}
+        torch.save({"global_step": int(iteration), "state_dict": sd,
+                    "optimizer": self.opt.state_dict() if self.opt is not None else None}, path)
+
+    def load_state(self, path, lr=None):
+        """R/uresnet/trainval.py:171-196: weights (strict=False), optimizer state when training, learning rate
+        reset to the current flag; returns the next iteration.  Works on a captured graph too: everything is
+        copied in place."""
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["state_dict"].items()}
+        own = self.net.state_dict()
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own:
+                    if v.dim() == own[k].dim() + 1 and v.shape[1] == 1:  # newer scn: [K, 1, nIn, nOut]
+                        v = v.squeeze(1)
+                    own[k].copy_(v)
+        if self.train and self.opt is not None and ck.get("optimizer") is not None:
+            keep = self.opt.lr if lr is None else lr
+            self.opt.load_state_dict(ck["optimizer"])
+            if hasattr(self.opt, "param_groups"):
+                for g in self.opt.param_groups:
+                    g["lr"] = keep
+            else:
+                self.opt.lr = float(keep)
+        scn_functional.repack_all()  # fragment-ordered weight copies follow the restored weights
+        torch.cuda.synchronize(self.device)
+        return int(ck["global_step"]) + 1
+
     @torch.no_grad()
     def infer(self, data_np):
         """Forward only: host blob in, logits [N, nc] on the device out (eager regime)."""
