@@ -199,7 +199,7 @@ int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, i
 /* Single-launch variants for inputs small enough to sit in the SMs' registers (every level of a bs=1 512^3
  * event): statistics, a grid-wide barrier and the apply phase in ONE co-resident grid (<= one CTA per SM), so
  * the matrix is read once and the second launch disappears.  `sync` = two uint32 of caller-owned device memory,
- * zero before the first use (barrier count + generation; every call leaves the count at zero), not shared by
+ * zero before the first use (word 0: wrapping arrival counter, back at zero after every call; word 1 reserved), not shared by
  * calls that may run concurrently; NULL, or an input too large (judged from n_expect, the rows a typical event
  * holds at this level, 0 = unknown), falls through to the two-kernel functions above.  Same results contract. */
 int b200scn_bn_fwd_train_sync(const float* x, int64_t ldx, int64_t n_cap, const int32_t* n_dev, int64_t n_expect,

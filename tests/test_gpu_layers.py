@@ -168,7 +168,7 @@ def test_batchnorm_single_launch_matches_two_kernel(n, c, live):
         y[:m].backward(dy[:m])
         torch.cuda.synchronize()
         res.append((y.detach()[:m], xx.grad[:m], ww.grad, bb.grad, rm, rv))
-    assert int(sync[0].item()) == 0 and int(sync[1].item()) in (0, 6)  # 3 forward + 3 backward barriers, or fallback
+    assert int(sync[0].item()) == 0  # the wrapping arrival counter is back at zero after every call
     xd = x[:m].double()
     mu, var = xd.mean(0), xd.var(0, unbiased=False)
     ref = torch.relu((xd - mu) / (var + 1e-4).sqrt() * w.double() + b.double())

@@ -359,7 +359,7 @@ __global__ void k_bn_merge_sums(const float* __restrict__ part, int64_t n_cap, c
 // ---- single-launch variants for inputs that fit the SMs' registers (every level of a bs=1 512^3 event) ------
 // One co-resident grid (<= one CTA per SM): statistics, a grid-wide barrier, then the apply phase on the SAME
 // registers -- the feature matrix is read once and the second launch (5-9 us of pure latency per layer at these
-// sizes) disappears.  The barrier state (count, generation) lives in caller memory that is zero before the first
+// sizes) disappears.  The barrier state (one wrapping counter) lives in caller memory that is zero before the first
 // use and is left zero-count by every launch; all CTAs are resident at once because the grid never exceeds the
 // SM count, so the spin cannot starve a CTA that has not started.
 constexpr int kFusedV = 8;  // values per thread cached in registers; rows beyond are re-read (L2 hits)
@@ -370,18 +370,16 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// One wrapping counter: atomicInc(cnt, G - 1) returns to zero with the G-th arrival, which is both the release
+// signal of this launch and the reset for the next one -- three L2 round trips per CTA (fence, atomic, one
+// poll) instead of the eight of a count + generation pair (ncu: the barrier was most of the kernel's 11 us).
 __device__ __forceinline__ void grid_barrier(unsigned int* sync, unsigned int G) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int gen = ld_acquire_u32(sync + 1);
     __threadfence();
-    const unsigned int old = atomicAdd(sync, 1u);
-    if (old == G - 1u) {
-      sync[0] = 0u;  // ready for the next launch
-      __threadfence();
-      atomicAdd(sync + 1, 1u);
-    } else {
-      while (ld_acquire_u32(sync + 1) == gen) {
+    const unsigned int old = atomicInc(sync, G - 1u);
+    if (old != G - 1u) {
+      while (ld_acquire_u32(sync) != 0u) {
       }
     }
     __threadfence();
