@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic steps cycled through")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2 = BASELINE configs[1] (the metric's config, default); c3 / c5 = configs[2] / configs[4]")
+    ap.add_argument("--no-bucket", action="store_true", help="keep the pool in generation order (no size bucketing)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep wgrad kernels on the main stream")
@@ -128,9 +129,16 @@ class ClockSampler(object):
 
 
 def make_pool(args, rank):
+    """`--pool` distinct synthetic steps per rank (rank r draws from its own stream).  Unless
+    --no-bucket is given the pool is ordered by voxel count on every rank -- size-bucketed sampling: the ranks
+    of one step then hold events of similar size, so the per-step gradient all-reduce waits less for the
+    largest event (same events, same total work; at N=1 only the order changes)."""
     from uresnet_pytorch_b200 import synthetic
     stream = synthetic.EventStream(args.events_per_gpu, CONFIG["ss"], CONFIG["dim"], rank=rank)
-    return [stream.next() for _ in range(args.pool)]
+    pool = [stream.next() for _ in range(args.pool)]
+    if not getattr(args, "no_bucket", False):
+        pool.sort(key=lambda dl: len(dl[0]))
+    return pool
 
 
 # ------------------------------------------------------------------------------------------------
@@ -386,6 +394,8 @@ def run_b200(args):
         "config": {"workload": WORKLOAD % args.events_per_gpu,
                    "events_per_gpu": args.events_per_gpu, "mean_voxels_per_step_per_gpu": vox_all / world / args.steps,
                    "cuda_graph": graph, "row_capacity": cap if graph else None,
+                   "sampling": "generation order" if args.no_bucket else "pool ordered by voxel count on every rank "
+                                                                         "(size-bucketed steps)",
                    "l2": "256 MB buffer written between timed steps (L2 flush), outside the CUDA events",
                    "timing": "sum of per-step CUDA-event durations, max over ranks", "wall_s": wall},
         "e2e": {"value": vox_e2e_all / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": h2d // args.steps,

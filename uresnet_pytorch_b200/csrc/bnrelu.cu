@@ -2,12 +2,15 @@
 // (/root/reference/uresnet/models/uresnet_sparse.py:23) and the BatchNormLeakyReLU layers
 // inside scn.UNet (:22).  Semantics per SURVEY.md 8(a) row a6 / Appendix A.7.
 //
-// Pure HBM-bound streaming over an [N, C] fp32 matrix.  Training forward = one statistics
-// pass (per-thread shifted sums, merged with Chan's formula in a fixed order so the result
-// is deterministic and as accurate as a two-pass variance) + one apply pass; the per-CTA
-// partials are folded by the last CTA to finish (ticket counter), so no extra launch and no
-// host involvement.  Thread layout: thread = (column c, row lane rl); consecutive threads
-// read consecutive columns of a row -> coalesced for any C.
+// Pure streaming over an [N, C] fp32 matrix.  Statistics are per-thread shifted sums merged with Chan's formula
+// in a fixed order, so the result is deterministic and as accurate as a two-pass variance.  Thread layout:
+// thread = (column c, row lane rl); consecutive threads read consecutive columns of a row -> coalesced for any C.
+// Two regimes:
+//   * small inputs (every level of a bs=1 512^3 event): ONE launch per direction -- statistics, a grid-wide
+//     barrier on a caller-owned wrapping counter, then the apply phase on the same registers
+//     (k_bn_fwd_fused / k_bn_bwd_fused, <= 64 co-resident CTAs);
+//   * large inputs: a statistics pass writing per-CTA partials + an apply pass whose CTAs fold them (every CTA in
+//     the same order; beyond 64 partials one CTA merges them first).
 #include <stdlib.h>
 
 #include "common.cuh"
