@@ -793,7 +793,16 @@ __global__ void k_pack_weights(const int64_t* __restrict__ jobs) {
 using namespace b200scn;
 
 /* tile rows the library recommends for a level of n rows */
-extern "C" int b200scn_gpl_tile_rows(int64_t n) { return n >= 12288 ? 128 : (n >= 5120 ? 64 : 32); }
+extern "C" int b200scn_gpl_tile_rows(int64_t n) {
+  static int64_t t128 = -1, t64 = -1;  // B200SCN_GPL_T128 / B200SCN_GPL_T64 override the row thresholds (A/B runs)
+  if (t128 < 0) {
+    const char* e = getenv("B200SCN_GPL_T128");
+    t128 = e ? atoll(e) : 12288;
+    e = getenv("B200SCN_GPL_T64");
+    t64 = e ? atoll(e) : 5120;
+  }
+  return n >= t128 ? 128 : (n >= t64 ? 64 : 32);
+}
 
 /* upper bound of the number of groups for n_cap rows (static regime allocation, fixed-stride lists) */
 extern "C" int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows) {
