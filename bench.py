@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=1)
-    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic steps cycled through")
+    ap.add_argument("--pool", type=int, default=10, help="distinct synthetic steps cycled through (30 default steps = 3 passes)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2 = BASELINE configs[1] (the metric's config, default); c3 / c5 = configs[2] / configs[4]")
     ap.add_argument("--no-bucket", action="store_true", help="keep the pool in generation order (no size bucketing)")

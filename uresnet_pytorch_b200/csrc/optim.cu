@@ -17,17 +17,40 @@ __global__ void k_adam(const int64_t* __restrict__ jobs, int32_t* __restrict__ s
   float* v = reinterpret_cast<float*>(j[3]);
   const int64_t n = j[4];
   const int t = *step_dev + 1;
-  // bias corrections in double: 1 - beta^t loses most of its bits in float for small t
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)t));
-  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)t));
-  const float step_size = lr / bc1;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const float ge = g[e];
-    const float me = beta1 * m[e] + (1.f - beta1) * ge;
-    const float ve = beta2 * v[e] + (1.f - beta2) * ge * ge;
+  // bias corrections in double (1 - beta^t loses most of its bits in float for small t), once per CTA
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    s_bc[0] = (float)(1.0 - pow((double)beta1, (double)t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+  }
+  __syncthreads();
+  const float bc2s = s_bc[1];
+  const float step_size = lr / s_bc[0];
+  auto upd = [&](float& pe, float ge, float& me, float& ve) {
+    me = beta1 * me + (1.f - beta1) * ge;
+    ve = beta2 * ve + (1.f - beta2) * ge * ge;
+    pe -= step_size * (me / (sqrtf(ve) / bc2s + eps));
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    float4 pe = reinterpret_cast<float4*>(p)[e], me = reinterpret_cast<float4*>(m)[e], ve = reinterpret_cast<float4*>(v)[e];
+    const float4 ge = reinterpret_cast<const float4*>(g)[e];
+    upd(pe.x, ge.x, me.x, ve.x);
+    upd(pe.y, ge.y, me.y, ve.y);
+    upd(pe.z, ge.z, me.z, ve.z);
+    upd(pe.w, ge.w, me.w, ve.w);
+    reinterpret_cast<float4*>(m)[e] = me;
+    reinterpret_cast<float4*>(v)[e] = ve;
+    reinterpret_cast<float4*>(p)[e] = pe;
+  }
+  for (int64_t e = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float pe = p[e], me = m[e], ve = v[e];
+    upd(pe, g[e], me, ve);
     m[e] = me;
     v[e] = ve;
-    p[e] -= step_size * (me / (sqrtf(ve) / bc2s + eps));
+    p[e] = pe;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -50,7 +73,7 @@ extern "C" int b200scn_adam_step(const int64_t* jobs_dev, int n_jobs, int64_t ma
   cudaStream_t st = (cudaStream_t)stream;
   if (n_jobs <= 0) return 0;
   B200_CHECK_ARG(n_jobs <= 65535, "adam_step: too many tensors");
-  int64_t gx = cdiv(max_elems < 1 ? 1 : max_elems, 256 * 4);
+  int64_t gx = cdiv(max_elems < 1 ? 1 : max_elems, 256 * 4 * 4);  // float4 per thread, ~4 per thread
   if (gx > 32) gx = 32;
   k_adam<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(jobs_dev, step_dev, ticket_dev, lr, beta1, beta2, eps);
   count_launches(1);
