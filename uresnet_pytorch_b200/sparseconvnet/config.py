@@ -38,6 +38,12 @@ gpl_rows_by_size = {}  # the calibrated row counts themselves (launch heuristics
 # static regime: levels below this capacity build their pair lists in one pass into fixed-stride slots
 gpl_fixed_stride_max_rows = 128 * 8 * 148
 
+# static regime: the rulebooks and pair lists of the COARSER levels are built on a side stream right after the input
+# level exists, while the main stream already runs the level-0 layers (metadata.Metadata._prefetch).  The list of
+# builds is recorded during the first static forward of a given (dimension, input size) and replayed afterwards.
+prefetch_rules = os.environ.get("B200SCN_PREFETCH_RULES", "1") != "0"
+md_plans = {}
+
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None
 

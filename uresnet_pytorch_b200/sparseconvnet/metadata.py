@@ -51,6 +51,12 @@ class Metadata(object):
         self.n_in_dev = None  # static regime: device count of valid input rows
         self.in2row = self.first_idx = self.seg_off = self.seg = None
         self._scratch = None
+        # rule prefetch (static regime): see _prefetch
+        self._input_size = None
+        self._plan_key = None
+        self._recording = None
+        self._prefetching = False
+        self._prefetch_event = None
 
     # -- helpers -----------------------------------------------------------------------
     def _scratch_for(self, n_cap):
@@ -107,7 +113,53 @@ class Metadata(object):
                 raise ValueError("coordinates / sample ids must be integers in [0, 65535)")
             lv.n = cnt
         self.levels[tuple(spatial_size)] = lv
+        self._input_size = tuple(spatial_size)
+        if self.static and config.prefetch_rules:
+            self._plan_key = (self.dimension, self._input_size)
+            plan = config.md_plans.get(self._plan_key)
+            if plan is None:
+                self._recording = config.md_plans[self._plan_key] = []
+            elif plan:
+                self._prefetch(plan)
         return lv
+
+    # -- rule prefetch --------------------------------------------------------------------
+    def _note(self, name, *args):
+        """Record a build request of the first static forward (the plan later forwards replay ahead of time)."""
+        if self._recording is not None and not self._prefetching:
+            ent = (name, args)
+            if ent not in self._recording:
+                self._recording.append(ent)
+
+    def _prefetch(self, plan):
+        """Build everything beyond the input level on the side stream (forked from and later joined to the
+        current stream with events, so it is capturable).  Builds that only concern the input level stay lazy on
+        the main stream: the first layers need them at once."""
+        from . import functional as F
+        plan = [(name, args) for name, args in plan
+                if not (name in ("subm_table", "subm_gpl") and tuple(args[0]) == self._input_size)]
+        if not plan:
+            return
+        main = torch.cuda.current_stream(self.device)
+        side = F._side_stream(self.device)
+        side.wait_stream(main)
+        self._prefetching = True
+        try:
+            with torch.cuda.stream(side):
+                for name, args in plan:
+                    getattr(self, name)(*args)
+                self._prefetch_event = side.record_event()
+        finally:
+            self._prefetching = False
+
+    def _join(self, spatial_size=None):
+        """Make the current stream wait for the prefetched builds before it touches anything but the input level."""
+        if self._prefetch_event is None or self._prefetching:
+            return
+        if spatial_size is not None and tuple(spatial_size) == self._input_size:
+            return
+        torch.cuda.current_stream(self.device).wait_event(self._prefetch_event)
+        self._prefetch_event = None
 
     def check_errors(self):
         """Static regime: the out-of-range flag can be polled after the step (one sync)."""
@@ -118,6 +170,7 @@ class Metadata(object):
     # -- rulebooks ----------------------------------------------------------------------
     def level(self, spatial_size):
         key = tuple(spatial_size)
+        self._join(key)
         if key not in self.levels:
             raise RuntimeError("no active sites registered for spatial size %s" % (key,))
         return self.levels[key]
@@ -126,6 +179,7 @@ class Metadata(object):
         return lv.n_dev.data_ptr() if lv.n is None else None
 
     def subm_table(self, spatial_size, filter_size):
+        self._note("subm_table", tuple(spatial_size), filter_size)
         lv = self.level(spatial_size)
         if filter_size not in lv.subm:
             K = filter_size ** self.dimension
@@ -139,6 +193,8 @@ class Metadata(object):
 
     def down_rules(self, in_size, out_size, stride):
         """Rules of Convolution(filter == stride): creates the coarser level on first use."""
+        self._note("down_rules", tuple(in_size), tuple(out_size), stride)
+        self._join()
         lv = self.level(in_size)
         if stride not in lv.down:
             K = stride ** self.dimension
@@ -203,6 +259,7 @@ class Metadata(object):
                     rows_hint=config.gpl_rows_by_size.get(size_key, 0) if self.static else 0)
 
     def subm_gpl(self, spatial_size, filter_size):
+        self._note("subm_gpl", tuple(spatial_size), filter_size)
         lv = self.level(spatial_size)
         key = ("subm", filter_size)
         if key not in lv.gpl:
@@ -212,6 +269,8 @@ class Metadata(object):
 
     def strided_gpl(self, in_size, out_size, stride):
         """(pair list over the coarse rows from the child table, pair list over the fine rows from parent/kofs)"""
+        self._note("strided_gpl", tuple(in_size), tuple(out_size), stride)
+        self._join()
         rules = self.down_rules(in_size, out_size, stride)
         fine, coarse = self.level(in_size), self.level(out_size)
         K = stride ** self.dimension

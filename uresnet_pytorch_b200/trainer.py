@@ -184,6 +184,7 @@ class Trainer(object):
         """Warm up on a side stream, then capture the whole step into one CUDA graph."""
         valid = None
         self._calibrate_tiles()
+        scn.config.md_plans.clear()  # the rule-prefetch plan is re-recorded by the first warm-up step below
 
         def step():
             nonlocal valid
