@@ -74,3 +74,25 @@ def test_shard_events_matches_reference_assignment():
             assert shard_events(n, world, r) == [i for i in range(n) if i // per == r]
     with pytest.raises(ValueError):
         shard_events(7, 2, 0)
+
+
+def test_bench_pool_is_size_bucketed_and_rank_specific():
+    """bench.make_pool: every rank draws its own event stream and orders its pool by voxel count,
+    so the ranks of one step hold events of similar size; --no-bucket keeps the generation order."""
+    import bench
+
+    class A(object):
+        events_per_gpu, pool, no_bucket = 1, 4, False
+
+    saved = dict(bench.CONFIG)
+    bench.CONFIG.update(ss=64, dim=3)
+    try:
+        p0, p1 = bench.make_pool(A, 0), bench.make_pool(A, 1)
+        A.no_bucket = True
+        q0 = bench.make_pool(A, 0)
+    finally:
+        bench.CONFIG.update(saved)
+    n0, n1 = [len(d) for d, _ in p0], [len(d) for d, _ in p1]
+    assert n0 == sorted(n0) and n1 == sorted(n1) and n0 != n1
+    assert sorted(len(d) for d, _ in q0) == n0  # same events, different order
+    assert all(d.shape[1] == 5 and l.shape == (len(d), 1) for d, l in p0)
