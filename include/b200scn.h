@@ -189,8 +189,8 @@ int b200scn_bn_fwd_eval(const float* x, int64_t ldx, int64_t n_cap, const int32_
                         const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float leak, float* y, int64_t ldy, void* stream);
 /* backward of the fused op; the activation mask is recomputed from x and the saved stats.
- * train != 0: batch-stat backward; train == 0: affine backward with fixed (mean, invstd).
- * dgamma / dbeta are written (not accumulated). */
+ * `train` is a bit set: bit 0 = batch-stat backward (0: affine backward with fixed (mean, invstd));
+ * bit 1 = dgamma / dbeta are ADDED to what the buffers hold (a persistent flat gradient buffer), else written. */
 int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t n_cap,
                    const int32_t* n_dev, int C, const float* gamma, const float* beta, const float* mean,
                    const float* invstd, float leak, int train, float* dx, int64_t lddx, float* dgamma,
@@ -217,6 +217,14 @@ int b200scn_bn_bwd_sync(const float* x, int64_t ldx, const float* dy, int64_t ld
  * (iv) input / output layers -- scn.InputLayer features (mode 3 sums) and scn.OutputLayer
  * (uresnet_sparse.py:20,24), forward and backward.
  * ------------------------------------------------------------------------------------- */
+/* Batch collation (replaces the host-side padding of /root/reference/uresnet/iotools/iotools_sparse.py:131-141):
+ * events back to back as int32 coords [N, D] (row stride ldc) + offsets_dev[nb + 1] (event e owns rows
+ * [offsets[e], offsets[e+1])) -> out [N, D + 1] int32 (row stride ldo) with the sample id first_id + e in the
+ * last column; N = offsets[nb] <= n_cap is also stored to n_out_dev (optional), ready to be the n_dev of the
+ * input layer. */
+int b200scn_collate(const int32_t* coords, int64_t ldc, const int32_t* offsets_dev, int nb, int D, int first_id,
+                    int64_t n_cap, int32_t* out, int64_t ldo, int32_t* n_out_dev, void* stream);
+
 /* dst[i, :] = src[idx[i], :]                        (OutputLayer fwd, InputLayer bwd) */
 int b200scn_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t n_cap, const int32_t* n_dev,
                         int C, float* dst, int64_t ldd, void* stream);
@@ -273,15 +281,35 @@ int b200scn_colsum(const float* x, int64_t ldx, int64_t n, int C, float* out, vo
  * over events -- plus the whole backward of that chain for an upstream gradient of 1.
  * feat [n, m] = OutputLayer rows; W [nc, m], bias [nc] (torch.nn.Linear layout); label [n] (float class ids,
  * as the reference ships them); ids = the sample-id column (dtype code as for b200scn_input_build, element
- * stride ld_ids); nb = number of events a sample id may name (ids outside [0, nb) are ignored).
- * Outputs: loss_acc[2] = {total_loss, total_acc}; optional logits [n, nc]; optional (training) dfeat [n, m],
- * dW [nc, m], db [nc].  Deterministic (integer counting pass, fixed-order partial sums). */
+ * stride ld_ids); nb = number of events a sample id may name.
+ * Outputs: loss_acc[4] = {total_loss, total_acc, rows whose sample id is outside [0, nb), rows whose label is
+ * outside [0, nc)} -- such rows contribute nothing (the reference would fail on them, uresnet_sparse.py:57-82);
+ * the two counts let the caller refuse the step without a second pass.  Optional logits [n, nc]; optional
+ * (training) dfeat [n, m], dW [nc, m], db [nc]; accumulate != 0 ADDS dW / db to what the buffers hold (a
+ * persistent flat gradient buffer).  Deterministic (integer counting pass, fixed-order partial sums). */
 int64_t b200scn_head_loss_scratch_bytes(int64_t n_cap, int m, int nc, int nb);
 int b200scn_head_loss(const float* feat, int64_t ldf, const float* W, const float* bias, const float* label,
                       int64_t ld_label, const float* pix_w, int64_t ld_pw, const void* ids, int id_dtype,
                       int64_t ld_ids, int64_t n_cap, const int32_t* n_dev, int m, int nc, int nb, float* logits,
                       int64_t ld_logits, float* loss_acc, float* dfeat, int64_t ld_dfeat, float* dW, float* db,
-                      void* scratch, int64_t scratch_bytes, void* stream);
+                      int accumulate, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Inference outputs: what /root/reference/uresnet/trainval.py:127-130 copies to the host
+ * after a forward pass -- logits ('segmentation') and softmax -- plus the argmax prediction and, when `label`
+ * and `metrics` are given, the per-event sums behind the accuracy / confusion part of compute_metrics_sparse
+ * (/root/reference/uresnet/utils.py:127-200).  metrics[nb][E], E = 4 + nc + 2 nc nc, per event:
+ *   [0] pixels  [1] correctly predicted pixels  [2] sum of -log softmax[label]  [3] sum of softmax[label]
+ *   [4 + c] sum of softmax[label] over pixels of true class c
+ *   [4 + nc + c nc + c2] pixels of true class c predicted as c2      (confusion_matrix)
+ *   [4 + nc + nc nc + c nc + c2] summed `energy` of those pixels     (energy_confusion_matrix; 0 without energy)
+ * Rows with a sample id outside [0, nb) or a label outside [0, nc) are skipped by the metrics.  Every output
+ * pointer is optional.  ids / energy: dtype codes as for b200scn_input_build, element strides.  nb * E <= 8192. */
+int64_t b200scn_head_predict_scratch_bytes(int64_t n_cap, int nc, int nb);
+int b200scn_head_predict(const float* feat, int64_t ldf, const float* W, const float* bias, const float* label,
+                         int64_t ld_label, const void* ids, int id_dtype, int64_t ld_ids, const void* energy,
+                         int energy_dtype, int64_t ld_energy, int64_t n_cap, const int32_t* n_dev, int m, int nc,
+                         int nb, float* logits, int64_t ld_logits, float* softmax, int64_t ld_softmax,
+                         int32_t* pred, double* metrics, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (viii) optimiser: torch.optim.Adam (defaults; /root/reference/uresnet/trainval.py:21-30,159-167) over all

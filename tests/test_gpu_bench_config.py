@@ -1,0 +1,177 @@
+"""Parity of the configuration bench.py measures, against the CPU oracle.
+
+bench.py runs `Trainer(graph=True, capacity=..., math_mode=MATH_TF32X3)` with every default on
+(whole-step CUDA graph over capacity-sized buffers, device-side row counts, grouped pair lists
+built in fixed-stride slots, packed weights, rule prefetch on the side stream, weight
+gradients overlapped on a side stream, programmatic dependent launch, fused head + loss, fused
+Adam) at the BASELINE configs.  These tests drive exactly that object at
+
+    c2  uresnet_sparse 3D  ss=512 uns=5 uf=16 bs=1     (BASELINE configs[1], the metric's config)
+    c3  uresnet_sparse 2D  ss=512 uns=5 uf=16 bs=16    (BASELINE configs[2])
+    c5' uresnet_sparse 3D  ss=768 uns=6 uf=32 bs=2     (BASELINE configs[4] with 2 events per GPU
+                                                        instead of 8: same widths 32..192, same
+                                                        kernels, oracle still finishes in seconds)
+
+over several steps on events of different sizes (including ones larger than the event the
+graph was calibrated and captured on), and compare per step: loss, accuracy, EVERY parameter
+gradient and every BatchNorm running statistic with `OracleUResNet` run from the same weights
+(reference semantics: /root/reference/uresnet/models/uresnet_sparse.py:19-37, 57-82).
+
+Tolerances are the fp32 ones of tests/test_gpu_mma.py (MATH_TF32X3 is fp32-equivalent):
+loss rel 1e-4, whole-gradient rel-L2 1e-3, per-tensor guard 2e-2, running stats rel-L2 1e-4.
+The achieved numbers are printed (pytest -s / the captured output on failure).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_l2
+from oracle.model import OracleUResNet, segmentation_loss
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL, GRAD_TOL, TENSOR_TOL, STAT_TOL = 1e-4, 1e-3, 2e-2, 1e-4
+
+CONFIGS = {
+    # name: (dim, ss, uns, uf, events per step, number of steps)
+    "c2": (3, 512, 5, 16, 1, 3),
+    "c3": (2, 512, 5, 16, 16, 2),
+    "c5_2ev": (3, 768, 6, 32, 2, 2),
+}
+
+
+def _flags(dim, ss, uns, uf):
+    from uresnet_pytorch_b200.model import Flags
+    return Flags(DATA_DIM=dim, SPATIAL_SIZE=ss, URESNET_FILTERS=uf, URESNET_NUM_STRIDES=uns, NUM_CLASS=5)
+
+
+def _pool(events, ss, dim, steps):
+    """`steps` batches in generation order; the FIRST one (the capture / calibration event) is made the smallest
+    so that later steps replay the graph on more rows than it was calibrated on."""
+    from uresnet_pytorch_b200 import synthetic
+    stream = synthetic.EventStream(events, ss, dim, rank=0)
+    pool = [stream.next() for _ in range(steps + 1)]
+    pool.sort(key=lambda dl: len(dl[0]))
+    return pool
+
+
+def _oracle_step(ref, data, label):
+    d, l = torch.from_numpy(data), torch.from_numpy(label)
+    ref.zero_grad(set_to_none=True)
+    out = ref(d)[0]
+    loss, acc = segmentation_loss(out, d, l)
+    loss.backward()
+    return float(loss.item()), float(acc)
+
+
+def _compare_step(tag, trainer, ref, data, label):
+    """Oracle from the trainer's CURRENT weights, then one trainer step; compare loss / acc / grads / stats."""
+    sd = {k: v.detach().cpu().clone() for k, v in trainer.net.state_dict().items()}
+    ref.load_state_dict(sd)
+    ref.train()
+    loss_ref, acc_ref = _oracle_step(ref, data, label)
+    r = trainer.train_step(data, label)
+    torch.cuda.synchronize()
+    assert np.isfinite(r["loss"])
+    assert abs(r["loss"] - loss_ref) <= LOSS_TOL * abs(loss_ref), (tag, r, loss_ref)
+    assert abs(r["acc"] - acc_ref) <= 2e-3, (tag, r, acc_ref)
+    g_ref = dict(ref.named_parameters())
+    num = den = 0.0
+    worst, worst_name = 0.0, None
+    for name, p in trainer.net.named_parameters():
+        assert p.grad is not None, name
+        a, b = p.grad.detach().double().cpu(), g_ref[name].grad.detach().double()
+        num += (a - b).pow(2).sum().item()
+        den += b.pow(2).sum().item()
+        e = rel_l2(a, b)
+        if e > worst:
+            worst, worst_name = e, name
+    glob = (num / max(den, 1e-300)) ** 0.5
+    b_ref = dict(ref.named_buffers())
+    stat = max(rel_l2(b, b_ref[n]) for n, b in trainer.net.named_buffers())
+    print("%s: rows %d loss %.6f (oracle %.6f) grad rel-L2 %.3g worst tensor %.3g (%s) running stats %.3g"
+          % (tag, len(data), r["loss"], loss_ref, glob, worst, worst_name, stat))
+    assert glob <= GRAD_TOL, (tag, glob)
+    assert worst <= TENSOR_TOL, (tag, worst_name, worst)
+    assert stat <= STAT_TOL, (tag, stat)
+    return r
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c5_2ev"])
+def test_benched_graph_trainer_matches_oracle(name):
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.trainer import Trainer
+    dim, ss, uns, uf, events, steps = CONFIGS[name]
+    flags = _flags(dim, ss, uns, uf)
+    pool = _pool(events, ss, dim, steps)
+    cap = max(len(d) for d, _ in pool)
+    cap = ((cap + cap // 8 + 4095) // 4096) * 4096          # bench.py's capacity rule
+    trainer = Trainer(flags, lr=1e-3, graph=True, capacity=cap, events_per_step=events,
+                      math_mode=scn.MATH_TF32X3, seed=0)     # bench.py's constructor call
+    torch.manual_seed(0)
+    ref = OracleUResNet(flags)
+    # capture on the smallest batch; its result is compared too (train_step captures, then replays)
+    losses = []
+    for i, (data, label) in enumerate(pool):
+        r = _compare_step("%s step %d" % (name, i), trainer, ref, data, label)
+        losses.append(r["loss"])
+    assert trainer._graph is not None
+    # replay a SMALLER batch after the larger ones: stale rows of the static buffers must not leak in
+    _compare_step("%s step again-0" % name, trainer, ref, *pool[0])
+
+
+def test_benched_graph_trainer_trajectory_matches_oracle_adam():
+    """Free-running: the graph trainer (fused Adam in the graph) and the oracle with torch.optim.Adam from the same
+    initial weights stay together over 4 steps at c2 (loss within 1e-3 at every step)."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.trainer import Trainer
+    dim, ss, uns, uf, events, _ = CONFIGS["c2"]
+    flags = _flags(dim, ss, uns, uf)
+    pool = _pool(events, ss, dim, 3)
+    cap = ((max(len(d) for d, _ in pool) * 9 // 8 + 4095) // 4096) * 4096
+    trainer = Trainer(flags, lr=1e-3, graph=True, capacity=cap, events_per_step=events,
+                      math_mode=scn.MATH_TF32X3, seed=0)
+    ref = OracleUResNet(flags)
+    ref.load_state_dict({k: v.detach().cpu().clone() for k, v in trainer.net.state_dict().items()})
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for i, (data, label) in enumerate(pool):
+        loss_ref, _ = _oracle_step(ref, data, label)
+        opt.step()
+        r = trainer.train_step(data, label)
+        print("trajectory step %d: loss %.6f oracle %.6f" % (i, r["loss"], loss_ref))
+        assert abs(r["loss"] - loss_ref) <= 1e-3 * abs(loss_ref), (i, r, loss_ref)
+    p_ref = dict(ref.named_parameters())
+    num = den = 0.0
+    for n, p in trainer.net.named_parameters():
+        a, b = p.detach().double().cpu(), p_ref[n].detach().double()
+        num += (a - b).pow(2).sum().item()
+        den += b.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 2e-3, (num / den) ** 0.5
+
+
+def test_bad_coordinates_are_reported_in_graph_mode():
+    """Static regime: an out-of-range coordinate / sample id / label raises from train_step (the flags ride on
+    the loss read-back), instead of training on garbage silently."""
+    from conftest import small_flags
+    from helpers import event_blob
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    data, label = event_blob(2, 32, seed=4)
+    t = Trainer(flags, graph=True, capacity=len(data) + 64, events_per_step=2, seed=1)
+    t.train_step(data, label)
+    bad = data.copy()
+    bad[3, 0] = -7.0
+    with pytest.raises(ValueError):
+        t.train_step(bad, label)
+    t.train_step(data, label)          # the trainer stays usable
+    bad = data.copy()
+    bad[5, 3] = 9.0                    # sample id >= events_per_step
+    with pytest.raises(ValueError):
+        t.train_step(bad, label)
+    badl = label.copy()
+    badl[7, 0] = 11.0                  # label >= NUM_CLASS
+    with pytest.raises(ValueError):
+        t.train_step(data, badl)
+    r = t.train_step(data, label)
+    assert np.isfinite(r["loss"])

@@ -126,15 +126,16 @@ def test_static_regime_matches_eager_forward_backward():
         assert rel_l2(p.grad, g_e[n]) <= 1e-4, n
 
 
-def test_graph_trainer_matches_eager_trainer():
+@pytest.mark.parametrize("mode,uf", [(0, 8), (1, 16)])
+def test_graph_trainer_matches_eager_trainer(mode, uf):
     """Whole-step CUDA graph (static regime, padded capacity) == eager step, over several
-    steps with different event sizes."""
+    steps with different event sizes; FP32 FFMA kernels and the tensor-core pair-list path."""
     from uresnet_pytorch_b200.trainer import Trainer
-    flags = small_flags()
+    flags = small_flags(URESNET_FILTERS=uf)
     blobs = [event_blob(2, 32, seed=s) for s in (1, 2, 3, 4)]
     cap = max(len(b[0]) for b in blobs) + 37
-    te = Trainer(flags, lr=1e-3, graph=False, events_per_step=2, seed=5)
-    tg = Trainer(flags, lr=1e-3, graph=True, capacity=cap, events_per_step=2, seed=5)
+    te = Trainer(flags, lr=1e-3, graph=False, events_per_step=2, seed=5, math_mode=mode)
+    tg = Trainer(flags, lr=1e-3, graph=True, capacity=cap, events_per_step=2, seed=5, math_mode=mode)
     for data, label in blobs:
         re_ = te.train_step(data, label)
         rg = tg.train_step(data, label)

@@ -1,0 +1,210 @@
+"""Trainer mechanics added with the flat gradient buffer (functional.GradSink): input formats, gradient
+accumulation over several forwards (R/uresnet/trainval.py:21-30,59-69), several trainers alive at once (the
+packed-weight copies and their job tables are per parameter / per trainer), pipelined submit/result, and the
+2-rank NCCL data-parallel step (R/uresnet/ops.py:8-60 semantics: gradients are SUMMED over replicas)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import small_flags
+from helpers import event_blob, rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compact(data, dim=3):
+    return (np.ascontiguousarray(data[:, :dim + 1], dtype=np.int32), np.ascontiguousarray(data[:, dim + 1], dtype=np.float32))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_compact_input_format_equals_reference_blob(graph):
+    """int32 coords + float32 values give bit-identical steps to the float64 wire format."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags(SPATIAL_SIZE=64, URESNET_FILTERS=16)
+    blobs = [event_blob(2, 64, seed=s, dup=7) for s in (1, 2, 3)]
+    cap = max(len(b[0]) for b in blobs) + 11
+    kw = dict(lr=1e-3, graph=graph, capacity=cap if graph else None, events_per_step=2, seed=5,
+              math_mode=scn.MATH_TF32X3)
+    a = Trainer(flags, input_format="blob64", **kw)
+    b = Trainer(flags, input_format="compact", **kw)
+    for data, label in blobs:
+        ra = a.train_step(data, label)
+        rb = b.train_step(_compact(data), label)
+        assert ra == rb, (ra, rb)
+    for (n, p), (_, q) in zip(a.net.named_parameters(), b.net.named_parameters()):
+        assert torch.equal(p, q), n
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_gradient_accumulation_matches_oracle(graph):
+    """train_step_accum: the gradient the optimiser sees is the mean over the forwards (trainval.py:21-30)."""
+    from oracle.model import OracleUResNet, segmentation_loss
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    blobs = [event_blob(2, 32, seed=s) for s in (1, 2, 3)]
+    cap = max(len(b[0]) for b in blobs) + 9
+    t = Trainer(flags, lr=1e-3, graph=graph, capacity=cap if graph else None, events_per_step=2, seed=5)
+    ref = OracleUResNet(flags)
+    ref.load_state_dict({k: v.detach().cpu().clone() for k, v in t.net.state_dict().items()})
+    ref.train()
+    tot = 0.0
+    for data, label in blobs:
+        d, l = torch.from_numpy(data), torch.from_numpy(label)
+        loss, _ = segmentation_loss(ref(d)[0], d, l)
+        tot = tot + loss
+    (tot / len(blobs)).backward()
+    r = t.train_step_accum(blobs)
+    torch.cuda.synchronize()
+    assert abs(r["loss"] - float(tot)) <= 1e-4 * abs(float(tot))
+    g_ref = dict(ref.named_parameters())
+    num = den = 0.0
+    for name, p in t.net.named_parameters():
+        a, b = p.grad.detach().double().cpu(), g_ref[name].grad.detach().double()
+        num += (a - b).pow(2).sum().item()
+        den += b.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 1e-3
+    # and a plain step afterwards starts from a clean buffer
+    before = t.train_step(*blobs[0])
+    assert np.isfinite(before["loss"])
+
+
+def test_two_graph_trainers_interleaved():
+    """Two captured trainers alive at once (the packed-weight job table of one must survive the other):
+    interleaved steps equal the same trainers run one after the other."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags(SPATIAL_SIZE=64, URESNET_FILTERS=16)
+    blobs = [event_blob(2, 64, seed=s) for s in (1, 2, 3)]
+    cap = max(len(b[0]) for b in blobs) + 11
+    kw = dict(lr=1e-3, graph=True, capacity=cap, events_per_step=2, math_mode=scn.MATH_TF32X3)
+
+    def solo(seed):
+        t = Trainer(flags, seed=seed, **kw)
+        out = [t.train_step(*b)["loss"] for b in blobs]
+        del t
+        return out
+
+    want_a, want_b = solo(5), solo(6)
+    a = Trainer(flags, seed=5, **kw)
+    la = [a.train_step(*blobs[0])["loss"]]
+    b = Trainer(flags, seed=6, **kw)
+    lb = []
+    for i in range(3):
+        lb.append(b.train_step(*blobs[i])["loss"])
+        if i + 1 < 3:
+            la.append(a.train_step(*blobs[i + 1])["loss"])
+    assert la == want_a and lb == want_b, (la, want_a, lb, want_b)
+
+
+def test_pipelined_submit_result_equals_synchronous():
+    from uresnet_pytorch_b200.trainer import Trainer
+    flags = small_flags()
+    blobs = [event_blob(2, 32, seed=s) for s in (1, 2, 3, 4, 5)]
+    cap = max(len(b[0]) for b in blobs) + 3
+    a = Trainer(flags, graph=True, capacity=cap, events_per_step=2, seed=2)
+    b = Trainer(flags, graph=True, capacity=cap, events_per_step=2, seed=2)
+    sync = [a.train_step(d, l) for d, l in blobs]
+    pipe, prev = [], None
+    for d, l in blobs:
+        t = b.submit(d, l)
+        if prev is not None:
+            pipe.append(b.result(prev))
+        prev = t
+    pipe.append(b.result(prev))
+    assert pipe == sync
+
+
+def test_eager_autograd_use_without_trainer_sees_optimizer_updates():
+    """FusedAdam writes through raw pointers; the packed-weight copies of eager scn modules must follow
+    (version counter bumped by FusedAdam.step)."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.optim import FusedAdam
+    data, _ = event_blob(2, 24, seed=3)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    torch.manual_seed(0)
+    lift = scn.NetworkInNetwork(1, 16, False).cuda()
+    conv = scn.SubmanifoldConvolution(3, 16, 16, 3, False).cuda()
+    opt = FusedAdam(list(conv.parameters()), lr=0.05)
+    feats = torch.randn(len(data), 1, device="cuda")
+    with scn.math(scn.MATH_TF32X3):
+        for _ in range(2):
+            x = scn.InputLayer(3, 24, mode=3)((coords, feats))
+            y = conv(lift(x)).features
+            conv.zero_grad()
+            y.square().sum().backward()
+            opt.step()
+        x = scn.InputLayer(3, 24, mode=3)((coords, feats))
+        h = lift(x)
+        y_packed = conv(h).features
+        scn.config.pack_weights = False
+        try:
+            y_plain = conv(h).features
+        finally:
+            scn.config.pack_weights = True
+    assert (y_packed - y_plain).abs().max().item() <= 1e-5 * y_plain.abs().max().item()
+
+
+_DP_WORKER = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import torch.distributed as dist
+from helpers import event_blob, rel_l2
+from uresnet_pytorch_b200 import sparseconvnet as scn
+from uresnet_pytorch_b200.model import Flags
+from uresnet_pytorch_b200.trainer import Trainer, init_distributed
+rank, local, world = init_distributed()
+flags = Flags(DATA_DIM=3, SPATIAL_SIZE=64, URESNET_FILTERS=16, URESNET_NUM_STRIDES=3, NUM_CLASS=5)
+blobs = [event_blob(1, 64, seed=10 * s + rank) for s in (1, 2, 3)]      # every rank its own events
+cap = 4096 * ((max(len(b[0]) for b in blobs) + 4095) // 4096)
+kw = dict(lr=1e-3, events_per_step=1, math_mode=scn.MATH_TF32X3, seed=0)
+dp = Trainer(flags, graph=True, capacity=cap, **kw)                       # captured step incl. NCCL all-reduce
+for step, (data, label) in enumerate(blobs):
+    # local gradient of this rank's event from the SAME weights, no communication
+    solo = Trainer(flags, graph=False, distributed=False, **kw)
+    solo.net.load_state_dict(dp.net.state_dict())
+    solo._fwd_bwd(*solo.upload(data, label), step=False)
+    g_local = solo.sink.flat.clone()
+    # reorder: both sinks use the same parameter order (same model), so flat buffers are comparable
+    dist.all_reduce(g_local, op=dist.ReduceOp.SUM)                         # what R/uresnet/ops.py reduce-adds
+    r = dp.train_step(data, label)
+    torch.cuda.synchronize()
+    err = rel_l2(dp.sink.flat, g_local)
+    assert err <= 1e-4, (step, err)
+    # replicas stay identical
+    chk = torch.stack([p.detach().double().sum() for p in dp.net.parameters()]).sum().reshape(1)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    assert all(torch.equal(both[0], b) for b in both), both
+    if rank == 0:
+        print("dp step %%d ok: loss %%.6f grad rel-L2 vs summed local grads %%.2e" %% (step, r["loss"], err))
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("DP_OK")
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_graph_step_sums_gradients():
+    """2 ranks over NCCL, whole step captured (all-reduce of the inner-level slice overlapped on the comm stream):
+    the gradient every replica applies == the SUM of the replicas' local gradients, replicas stay identical."""
+    code = _DP_WORKER % dict(root=ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", _write_worker(code)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _write_worker(code):
+    import tempfile
+    f = tempfile.NamedTemporaryFile("w", suffix="_dp_worker.py", delete=False)
+    f.write(code)
+    f.close()
+    return f.name

@@ -118,3 +118,20 @@ def test_oracle_matches_golden():
     assert np.allclose(out.detach().numpy(), g["logits"], atol=2e-5, rtol=1e-4)
     assert abs(loss.item() - float(g["loss"])) < 1e-5
     assert np.allclose(m.sparseModel[1].weight.grad.numpy(), g["grad_stem"], atol=1e-5, rtol=1e-3)
+
+
+def test_metrics_oracle_matches_reference_golden():
+    """oracle/metrics.py against outputs of the UNMODIFIED reference function (utils.py:78), generated by
+    tests/golden/make_metrics_golden.py."""
+    import os
+    import numpy as np
+    from oracle import metrics as om
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_small.npz"))
+    with np.errstate(all="ignore"):
+        res = om.compute_metrics_sparse([g["data"]], [g["label"]], [g["softmax"]])
+    for k in ("acc", "correct_softmax", "id", "nonzero_pixels", "class_acc", "class_pixel", "class_mean_softmax",
+              "confusion_matrix", "energy_confusion_matrix", "loss_seg"):
+        got = np.array([np.asarray(v, dtype=np.float64).reshape(-1) if np.ndim(v) else float(v) for v in res[k]])
+        ref = g["ref." + k]
+        assert got.shape == ref.shape, k
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True), (k, got, ref)

@@ -39,7 +39,10 @@ SIGNATURES = {
     "b200scn_adam_step": (_I32, [_P, _I32, _I64, _P, _P, _F32, _F32, _F32, _F32, _P]),
     "b200scn_head_loss_scratch_bytes": (_I64, [_I64, _I32, _I32, _I32]),
     "b200scn_head_loss": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I32, _I64, _I64, _P, _I32, _I32, _I32, _P,
-                                 _I64, _P, _P, _I64, _P, _P, _P, _I64, _P]),
+                                 _I64, _P, _P, _I64, _P, _P, _I32, _P, _I64, _P]),
+    "b200scn_head_predict_scratch_bytes": (_I64, [_I64, _I32, _I32]),
+    "b200scn_head_predict": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I32, _I64, _P, _I32, _I64, _I64, _P, _I32, _I32,
+                                    _I32, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P]),
     "b200scn_conv_table": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _I32, _P, _I64, _I32, _I64, _P, _I32, _I32, _P,
                                   _I64, _I32, _I32, _P]),
     "b200scn_conv_parent": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I64, _P, _I32, _I32, _P, _I64,
@@ -57,6 +60,7 @@ SIGNATURES = {
                                          _P, _P, _P, _I64, _P]),
     "b200scn_bn_bwd_sync": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I64, _I32, _P, _P, _P, _P, _F32, _I32, _P, _I64, _P,
                                    _P, _P, _P, _I64, _P]),
+    "b200scn_collate": (_I32, [_P, _I64, _P, _I32, _I32, _I32, _I64, _P, _I64, _P, _P]),
     "b200scn_gather_rows": (_I32, [_P, _I64, _P, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_segsum_rows": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_add_rows": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I32, _P, _I64, _P]),

@@ -288,14 +288,19 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ x, int64_t ldx, const f
     a2 += sm[T + j * C + c];
   }
   if (blockIdx.x == 0 && rl == 0) {
-    dbeta[c] = a1;
-    dgamma[c] = a2;
+    if (train & 2) {  // accumulate into a persistent gradient buffer (functional.GradSink)
+      dbeta[c] += a1;
+      dgamma[c] += a2;
+    } else {
+      dbeta[c] = a1;
+      dgamma[c] = a2;
+    }
   }
   const float mu = mean[c], is = invstd[c];
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
-  const float k1 = train ? a1 * inv_n : 0.f;
-  const float k2 = train ? a2 * inv_n : 0.f;
+  const float k1 = (train & 1) ? a1 * inv_n : 0.f;
+  const float k2 = (train & 1) ? a2 * inv_n : 0.f;
   const float gi = g * is;
   for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
     const float xh = (__ldg(x + (int64_t)r * ldx + c) - mu) * is;
@@ -581,12 +586,17 @@ k_bn_bwd_fused(const float* __restrict__ x, int64_t ldx, const float* __restrict
     a2 += sm[T + j * C + c];
   }
   if (blockIdx.x == 0 && rl == 0) {
-    dbeta[c] = a1;
-    dgamma[c] = a2;
+    if (train & 2) {  // accumulate into a persistent gradient buffer (functional.GradSink)
+      dbeta[c] += a1;
+      dgamma[c] += a2;
+    } else {
+      dbeta[c] = a1;
+      dgamma[c] = a2;
+    }
   }
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
-  const float k1 = train ? a1 * inv_n : 0.f;
-  const float k2 = train ? a2 * inv_n : 0.f;
+  const float k1 = (train & 1) ? a1 * inv_n : 0.f;
+  const float k2 = (train & 1) ? a2 * inv_n : 0.f;
   const float gi = g * is;
 #pragma unroll
   for (int v = 0; v < kFusedV; ++v) {
@@ -703,8 +713,10 @@ extern "C" int b200scn_bn_bwd(const float* x, int64_t ldx, const float* dy, int6
   B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
   B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_bwd: scratch too small");
   if (n_cap == 0) {
-    B200_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
-    B200_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+    if (!(train & 2)) {
+      B200_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
+      B200_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+    }
     return 0;
   }
   Layout L = make_layout(n_cap, C);

@@ -46,6 +46,25 @@ __global__ void k_add_rows(const float* __restrict__ a, int64_t lda, const float
   }
 }
 
+// Collation (/root/reference/uresnet/iotools/iotools_sparse.py:131-141 pads every event's
+// voxels with its batch id on the host and concatenates in float64): events arrive back to back as int32
+// coordinates [N, D] plus event offsets; the kernel writes the [N, D + 1] matrix the input layer reads, the sample
+// id found by a binary search over the (few) offsets.
+__global__ void k_collate(const int32_t* __restrict__ coords, int64_t ldc, const int32_t* __restrict__ offsets, int nb,
+                          int D, int first_id, int32_t* __restrict__ out, int64_t ldo, int32_t* __restrict__ n_out) {
+  const int n = __ldg(offsets + nb);
+  if (n_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nb;  // last event whose offset is <= r
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid) <= r) lo = mid; else hi = mid;
+    }
+    for (int d = 0; d < D; ++d) out[r * ldo + d] = __ldg(coords + r * ldc + d);
+    out[r * ldo + D] = first_id + lo;
+  }
+}
+
 inline int ew_grid(int64_t elems) {
   int64_t g = cdiv(elems, 256);
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -88,5 +107,16 @@ extern "C" int b200scn_add_rows(const float* a, int64_t lda, const float* b, int
   k_add_rows<<<ew_grid(n_cap * C), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n_cap, n_dev, C, out, ldo);
   count_launches(1);
   B200_CHECK_LAUNCH("add_rows");
+  return 0;
+}
+
+extern "C" int b200scn_collate(const int32_t* coords, int64_t ldc, const int32_t* offsets_dev, int nb, int D,
+                               int first_id, int64_t n_cap, int32_t* out, int64_t ldo, int32_t* n_out_dev,
+                               void* stream) {
+  B200_CHECK_ARG(nb >= 1 && D >= 1 && D <= 3 && ldo >= D + 1 && ldc >= D, "collate: bad shape");
+  k_collate<<<ew_grid(n_cap < 1 ? 1 : n_cap), 256, 0, (cudaStream_t)stream>>>(coords, ldc, offsets_dev, nb, D, first_id,
+                                                                            out, ldo, n_out_dev);
+  count_launches(1);
+  B200_CHECK_LAUNCH("collate");
   return 0;
 }

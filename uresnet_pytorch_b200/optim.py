@@ -45,6 +45,16 @@ class FusedAdam(object):
             t.zero_()
         self.step_dev.zero_()
 
+    def snapshot(self):
+        """Copy of the moments and the step count (graph capture warms up on real steps, then puts this back)."""
+        return ([t.clone() for t in self.exp_avg], [t.clone() for t in self.exp_avg_sq], self.step_dev.clone())
+
+    @torch.no_grad()
+    def restore(self, snap):
+        for dst, src in zip(self.exp_avg + self.exp_avg_sq, snap[0] + snap[1]):
+            dst.copy_(src)
+        self.step_dev.copy_(snap[2])
+
     @torch.no_grad()
     def step(self):
         live = [i for i, p in enumerate(self.params) if p.grad is not None]
@@ -64,6 +74,9 @@ class FusedAdam(object):
         self._keep = host
         _lib.call("b200scn_adam_step", jobs.data_ptr(), n, self._max, self.step_dev.data_ptr(), self.ticket.data_ptr(),
                   self.lr, self.betas[0], self.betas[1], self.eps, torch.cuda.current_stream().cuda_stream)
+        # the kernel wrote through raw pointers: tell autograd (and the packed-weight caches keyed on the version
+        # counter, functional.packed_weights) that the parameters changed
+        torch.autograd.graph.increment_version([self.params[i] for i in live])
 
     # ------------------------------------------------------------------------------------
     def state_dict(self):

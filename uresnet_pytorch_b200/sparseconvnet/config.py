@@ -44,6 +44,10 @@ gpl_fixed_stride_max_rows = 128 * 8 * 148
 prefetch_rules = os.environ.get("B200SCN_PREFETCH_RULES", "1") != "0"
 md_plans = {}
 
+# set by a trainer: called with a tag when the backward pass of a MarkedSequential (the part of scn.UNet below
+# the first level) has completed -- the point where most gradient bytes exist and their all-reduce can start
+backward_mark_callback = None
+
 # static regime only: int32 device tensor[1] holding the number of valid input rows (None = all rows)
 static_input_rows = None
 

@@ -49,9 +49,69 @@ def join_side_streams():
     del _side_keepalive[:]
 
 
-def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=False):
+class GradSink(object):
+    """One flat fp32 gradient buffer with a view per parameter (the buffer the per-step NCCL
+    all-reduce runs over, replacing /root/reference/uresnet/ops.py:8-60's per-replica reduce-add).
+
+    While a sink is ACTIVE (`with sink.active():`) the backward kernels of this package write -- always
+    accumulating -- straight into the parameter's view and hand autograd no gradient tensor at all; `p.grad`
+    IS that view, permanently.  `zero()` (one memset of the flat buffer) starts a new accumulation, so several
+    forwards can be accumulated before one optimiser step (R/uresnet/trainval.py:21-30,59-69), a weight used
+    twice sums correctly, and parameters whose gradient arrives through plain torch autograd (an unfused
+    torch.nn.Linear head) accumulate into the same memory.  Because nothing consumes the views before the owner
+    has joined the side streams, weight-gradient kernels may run on a side stream without racing autograd."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # every view starts 16-byte aligned
+        self.flat = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        self.numel = total
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        self.offsets = offs
+        self._on = False
+        for p, v in zip(self.params, self.views):
+            p._b200_sink = (self, v)
+            p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+
+    def active(self):
+        return _SinkScope(self)
+
+
+class _SinkScope(object):
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        self.prev = self.sink._on
+        self.sink._on = True
+        for p, v in zip(self.sink.params, self.sink.views):
+            if p.grad is not v:     # zero_grad(set_to_none=True) or an optimiser replaced it
+                p.grad = v
+        return self.sink
+
+    def __exit__(self, *exc):
+        self.sink._on = self.prev
+
+
+def _sink_view(param):
+    """The active sink's view for `param`, or None (-> the gradient goes back through autograd)."""
+    ent = getattr(param, "_b200_sink", None) if param is not None else None
+    if ent is not None and ent[0]._on:
+        return ent[1]
+    return None
+
+
+def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=False, sink=None):
     """dW [K, Ca, Cb].  `gpl`: the layer's FORWARD pair list (its out rows index B) -- when given, and the
-    shapes allow, the weight gradient walks it (csrc/wgrad_gpl.cu) instead of re-compacting the table."""
+    shapes allow, the weight gradient walks it (csrc/wgrad_gpl.cu) instead of re-compacting the table.
+    `sink`: accumulate into this preallocated view (GradSink) and return None."""
     Ca, Cb = A.shape[1], B.shape[1]
     L = _lib.load()
     use_gpl = (gpl is not None and gpl.get("koff") is not None and config.use_gpl and config.wgrad_gpl and math != 0
@@ -61,29 +121,32 @@ def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=
 
     # every buffer is allocated on the main stream; only the kernels move to the side stream
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
-    dW = torch.empty(w_shape, dtype=torch.float32, device=A.device)
+    dW = sink if sink is not None else torch.empty(w_shape, dtype=torch.float32, device=A.device)
+    acc = 1 if sink is not None else 0
 
     def run():
         if use_gpl:
             _lib.call("b200scn_wgrad_gpl", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), gpl["tile_rows"],
                       gpl["g_rec"].data_ptr(), gpl["koff"].data_ptr(), K, int(subm), rows, n_dev,
-                      gpl.get("rows_hint", 0), Ca, Cb, dW.data_ptr(), 0, math, scratch.data_ptr(), nbytes, _stream())
+                      gpl.get("rows_hint", 0), Ca, Cb, dW.data_ptr(), acc, math, scratch.data_ptr(), nbytes, _stream())
             return
         _lib.call("b200scn_wgrad_table", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
-                  table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), 0,
+                  table.stride(0) if table is not None else 0, K, gather_b, rows, n_dev, Ca, Cb, dW.data_ptr(), acc,
                   math, scratch.data_ptr(), nbytes, _stream())
 
-    if not config.overlap_wgrad:
+    # Side-stream overlap only with a sink: a gradient tensor handed to autograd is consumed (AccumulateGrad,
+    # hooks, a second backward) on the main stream before anybody joins the side stream.
+    if not (config.overlap_wgrad and sink is not None):
         run()
-        return dW
+        return None if sink is not None else dW
     main = torch.cuda.current_stream(A.device)
     side = _side_stream(A.device)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         run()
-    _side_keepalive.append((scratch, A, B, table, gpl))
+    _side_keepalive.append((scratch, A, B, table, gpl, dW))
     _side_dirty.add((A.device.type, A.device.index))
-    return dW
+    return None
 
 
 def _gpl_ok(gpl, x, Cin, Cout, math):
@@ -91,62 +154,58 @@ def _gpl_ok(gpl, x, Cin, Cout, math):
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
 
 
-# Fragment-ordered weight copies (b200scn_pack_weights), one per (weight storage, direction).  An entry is
-# re-packed when the weight's version counter moved; a trainer that steps the optimiser inside a CUDA graph
-# calls repack_all() right after it, so the (captured) forward never finds a stale copy.
-_pack_cache = {}
-_pack_all_jobs = None
-
-
-def _pack_entry(W3, Cin, Cout, w_si, w_so, kflip):
-    key = (W3.data_ptr(), w_so == 1, kflip)
-    ent = _pack_cache.get(key)
-    if ent is None or ent["shape"] != tuple(W3.shape) or ent["device"] != W3.device:
-        global _pack_all_jobs
+# Fragment-ordered weight copies (b200scn_pack_weights), one per (weight, direction).  The copies live ON the
+# parameter object (`_b200_pack`), so they are freed with it and two models never see each other's entries.  A
+# copy is refreshed when the weight's version counter moved; whoever updates weights behind autograd's back
+# (FusedAdam writes through raw pointers, inside a CUDA graph) calls `repack_params` right after, which refreshes
+# every copy of the given parameters with ONE launch over a job table it returns -- the caller keeps that table
+# alive as long as a captured graph may replay the launch.
+def _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip):
+    cache = getattr(W, "_b200_pack", None)
+    if cache is None:
+        cache = W._b200_pack = {}
+    key = (w_so == 1, kflip)
+    ent = cache.get(key)
+    if ent is None or ent["ptr"] != W3.data_ptr() or ent["shape"] != tuple(W3.shape):
         K = W3.shape[0]
         buf = torch.empty(K * Cin * Cout, dtype=torch.float32, device=W3.device)
         job = torch.tensor([W3.data_ptr(), buf.data_ptr(), K, Cin, Cout, W3.shape[1] * W3.shape[2], w_si, w_so, kflip,
                             0], dtype=torch.int64).to(W3.device)
-        ent = dict(shape=tuple(W3.shape), device=W3.device, buf=buf, job=job, version=None, W=W3,
-                   elems=K * Cin * Cout)
-        _pack_cache[key] = ent
-        _pack_all_jobs = None
+        ent = dict(ptr=W3.data_ptr(), shape=tuple(W3.shape), buf=buf, job=job, version=None, elems=K * Cin * Cout)
+        cache[key] = ent
     return ent
 
 
-def packed_weights(W3, Cin, Cout, w_si, w_so, kflip):
-    """Device pointer of the fragment-ordered copy of W3 for the direction (Cin, Cout, w_si, w_so, kflip)."""
-    ent = _pack_entry(W3, Cin, Cout, w_si, w_so, kflip)
-    if ent["version"] != W3._version:
+def packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip):
+    """Device pointer of the fragment-ordered copy of W3 (a view of parameter W) for one direction."""
+    ent = _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip)
+    if ent["version"] != W._version:
         _lib.call("b200scn_pack_weights", ent["job"].data_ptr(), 1, ent["elems"], _stream())
-        ent["version"] = W3._version
+        ent["version"] = W._version
     return ent["buf"].data_ptr()
 
 
-def repack_all():
-    """Refresh every cached copy with ONE launch (after an optimiser step / a state-dict load)."""
-    global _pack_all_jobs
-    if not _pack_cache:
-        return
-    ents = list(_pack_cache.values())
-    if _pack_all_jobs is None:
-        _pack_all_jobs = torch.cat([e["job"] for e in ents])
-    _lib.call("b200scn_pack_weights", _pack_all_jobs.data_ptr(), len(ents), max(e["elems"] for e in ents), _stream())
-    for e in ents:
-        e["version"] = e["W"]._version
+def repack_params(params, jobs=None):
+    """Refresh every cached copy of `params` with ONE launch.  Returns the job table (pass it back in to
+    reuse it; it is rebuilt only when the set of copies changed)."""
+    ents = [e for p in params for e in getattr(p, "_b200_pack", {}).values()]
+    if not ents:
+        return jobs
+    ids = tuple(id(e) for e in ents)
+    if jobs is None or jobs[0] != ids:
+        jobs = (ids, torch.cat([e["job"] for e in ents]), max(e["elems"] for e in ents), ents)
+    _lib.call("b200scn_pack_weights", jobs[1].data_ptr(), len(ents), jobs[2], _stream())
+    for p in params:
+        for e in getattr(p, "_b200_pack", {}).values():
+            e["version"] = p._version
+    return jobs
 
 
-def clear_pack_cache():
-    global _pack_all_jobs
-    _pack_cache.clear()
-    _pack_all_jobs = None
-
-
-def _conv_gpl(x, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
+def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
     """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
-    Wp = packed_weights(W3, Cin, Cout, w_si, w_so, kflip) if config.pack_weights else None
+    Wp = packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip) if config.pack_weights else None
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
               kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
               n_out, n_out_dev, gpl.get("rows_hint", 0),
@@ -169,7 +228,7 @@ class TableConv(torch.autograd.Function):
         K, Cin, Cout = W3.shape
         math = config.math_mode
         if _gpl_ok(gpl_fwd, x, Cin, Cout, math):
-            out = _conv_gpl(x, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math)
+            out = _conv_gpl(x, W, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math)
         else:
             out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
             _lib.call("b200scn_conv_table", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1, 0,
@@ -178,6 +237,7 @@ class TableConv(torch.autograd.Function):
         ctx.save_for_backward(x, W3)
         ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math, gpl_bwd)
         ctx.gpl_fwd = gpl_fwd
+        ctx.w_param = W
         return out
 
     @staticmethod
@@ -189,7 +249,8 @@ class TableConv(torch.autograd.Function):
         dx = dW = None
         if ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
             # same pair structure, transposed weights; the symmetric (submanifold) list needs the offset flip
-            dx = _conv_gpl(dout, W3, 1, Cout, 1 if symmetric else 0, gpl_bwd, n_in, n_in_dev, Cout, Cin, math)
+            dx = _conv_gpl(dout, ctx.w_param, W3, 1, Cout, 1 if symmetric else 0, gpl_bwd, n_in, n_in_dev, Cout, Cin,
+                           math)
         elif ctx.needs_input_grad[0]:
             dx = torch.empty((n_in, Cin), dtype=torch.float32, device=x.device)
             if table is None or symmetric:
@@ -203,7 +264,8 @@ class TableConv(torch.autograd.Function):
                           parent.data_ptr(), kofs.data_ptr(), K, n_in, n_in_dev, Cout, Cin, dx.data_ptr(),
                           dx.stride(0), math, _stream())
         if ctx.needs_input_grad[1]:
-            dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math, ctx.gpl_fwd, symmetric)
+            dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math, ctx.gpl_fwd, symmetric,
+                        sink=_sink_view(ctx.w_param))
         return dx, dW, None, None, None, None, None, None, None, None, None, None
 
 
@@ -219,7 +281,7 @@ class ParentConv(torch.autograd.Function):
         K, Cin, Cout = W3.shape
         math = config.math_mode
         if _gpl_ok(gpl_fwd, x, Cin, Cout, math):
-            out = _conv_gpl(x, W3, Cout, 1, 0, gpl_fwd, n_fine, n_fine_dev, Cin, Cout, math)
+            out = _conv_gpl(x, W, W3, Cout, 1, 0, gpl_fwd, n_fine, n_fine_dev, Cin, Cout, math)
         else:
             out = torch.empty((n_fine, Cout), dtype=torch.float32, device=x.device)
             _lib.call("b200scn_conv_parent", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1,
@@ -228,6 +290,7 @@ class ParentConv(torch.autograd.Function):
         ctx.save_for_backward(x, W3)
         ctx.misc = (parent, kofs, child, n_fine, n_fine_dev, n_coarse, n_coarse_dev, math, gpl_bwd)
         ctx.gpl_fwd = gpl_fwd
+        ctx.w_param = W
         return out
 
     @staticmethod
@@ -238,7 +301,7 @@ class ParentConv(torch.autograd.Function):
         K, Cin, Cout = W3.shape
         dx = dW = None
         if ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
-            dx = _conv_gpl(dout, W3, 1, Cout, 0, gpl_bwd, n_coarse, n_coarse_dev, Cout, Cin, math)
+            dx = _conv_gpl(dout, ctx.w_param, W3, 1, Cout, 0, gpl_bwd, n_coarse, n_coarse_dev, Cout, Cin, math)
         elif ctx.needs_input_grad[0]:
             # dx[j] = sum_k dout[child[k][j]] @ W[k]^T
             dx = torch.empty((n_coarse, Cin), dtype=torch.float32, device=x.device)
@@ -249,9 +312,11 @@ class ParentConv(torch.autograd.Function):
             # dW[k] = sum_j x[j]^T @ dout[child[k][j]]
             if ctx.gpl_fwd is not None and ctx.gpl_fwd.get("koff") is not None:
                 # the forward list runs over the FINE rows (in = parent row, out = fine row): rows = n_fine
-                dW = _wgrad(x, dout, child, K, 1, n_fine, n_fine_dev, W3.shape, math, ctx.gpl_fwd, False)
+                dW = _wgrad(x, dout, child, K, 1, n_fine, n_fine_dev, W3.shape, math, ctx.gpl_fwd, False,
+                            sink=_sink_view(ctx.w_param))
             else:
-                dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math)
+                dW = _wgrad(x, dout, child, K, 1, n_coarse, n_coarse_dev, W3.shape, math,
+                            sink=_sink_view(ctx.w_param))
         return dx, dW, None, None, None, None, None, None, None, None, None
 
 
@@ -284,6 +349,7 @@ class BatchNormAct(torch.autograd.Function):
                       y.stride(0), _stream())
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.misc = (leak, training, rows, n_dev, sync, rows_hint)
+        ctx.params = (weight, bias)
         return y
 
     @staticmethod
@@ -296,12 +362,17 @@ class BatchNormAct(torch.autograd.Function):
         nbytes = L.b200scn_bn_scratch_bytes(rows, C)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         dx = torch.empty((rows, C), dtype=torch.float32, device=x.device)
-        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        # affine gradients: straight into the trainer's flat gradient buffer when one is active
+        sg, sb = _sink_view(ctx.params[0]), _sink_view(ctx.params[1])
+        sunk = sg is not None and sb is not None
+        dgamma = sg if sunk else torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = sb if sunk else torch.empty(C, dtype=torch.float32, device=x.device)
         _lib.call("b200scn_bn_bwd_sync", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), rows, n_dev,
                   rows_hint, C, _lib.ptr(weight), _lib.ptr(bias), mean.data_ptr(), invstd.data_ptr(), leak,
-                  int(training), dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(sync),
-                  scratch.data_ptr(), nbytes, _stream())
+                  int(training) | (2 if sunk else 0), dx.data_ptr(), dx.stride(0), dgamma.data_ptr(),
+                  dbeta.data_ptr(), _lib.ptr(sync), scratch.data_ptr(), nbytes, _stream())
+        if sunk:
+            dgamma = dbeta = None
         return (dx, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
                 None, None, None, None, None, None, None)
 
@@ -361,38 +432,42 @@ class OutputGather(torch.autograd.Function):
 
 class HeadLoss(torch.autograd.Function):
     """Fused Linear(m -> nc) + per-event mean cross-entropy + per-event accuracy (csrc/headloss.cu;
-    reference: uresnet_sparse.py:25,36,44-82).  Returns a tensor [2] = (total_loss, total_acc).  The
-    backward pass was already computed by the forward kernel for an upstream gradient of 1 on total_loss;
-    `backward` scales it by the incoming gradient of element 0."""
+    reference: uresnet_sparse.py:25,36,44-82).  Returns a tensor [4] = (total_loss, total_acc, rows with a
+    sample id outside [0, nb), rows with a label outside [0, nc)).  The backward pass was already computed by
+    the forward kernel for an upstream gradient of 1 on total_loss; `backward` scales it by the incoming
+    gradient of element 0."""
 
     @staticmethod
     def forward(ctx, feat, W, b, label, ids, nb, pix_w, rows, n_dev, unit_grad):
         _check_cuda_f32(feat, W, b)
         feat = _rowmajor(feat)
-        W = W.contiguous()
+        Wc = W.contiguous()
         label = label.reshape(-1)
         if label.dtype != torch.float32:
             label = label.float()
         if ids.dtype not in (torch.int32, torch.int64, torch.float32, torch.float64):
             ids = ids.long()
         codes = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
-        m, nc = feat.shape[1], W.shape[0]
+        m, nc = feat.shape[1], Wc.shape[0]
         L = _lib.load()
         nbytes = L.b200scn_head_loss_scratch_bytes(rows, m, nc, nb)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
-        out = torch.empty(2, dtype=torch.float32, device=feat.device)
+        out = torch.empty(4, dtype=torch.float32, device=feat.device)
         need = feat.requires_grad or W.requires_grad
         dfeat = torch.empty((rows, m), dtype=torch.float32, device=feat.device) if need else None
-        dW = torch.empty_like(W) if need else None
-        db = torch.empty(nc, dtype=torch.float32, device=feat.device) if need else None
+        # with an upstream gradient of exactly 1 the parameter gradients can go straight into the flat buffer
+        sW, sb = (_sink_view(W), _sink_view(b)) if (need and unit_grad and b is not None and Wc is W) else (None, None)
+        sunk = sW is not None and sb is not None
+        dW = (sW if sunk else torch.empty_like(Wc)) if need else None
+        db = (sb if sunk else torch.empty(nc, dtype=torch.float32, device=feat.device)) if need else None
         if pix_w is not None:
             pix_w = pix_w.reshape(-1).float()
-        _lib.call("b200scn_head_loss", feat.data_ptr(), feat.stride(0), W.data_ptr(), _lib.ptr(b), label.data_ptr(),
+        _lib.call("b200scn_head_loss", feat.data_ptr(), feat.stride(0), Wc.data_ptr(), _lib.ptr(b), label.data_ptr(),
                   label.stride(0), _lib.ptr(pix_w), pix_w.stride(0) if pix_w is not None else 0, ids.data_ptr(),
                   codes[ids.dtype], ids.stride(0), rows, n_dev, m, nc, nb, None, 0, out.data_ptr(), _lib.ptr(dfeat),
-                  dfeat.stride(0) if dfeat is not None else 0, _lib.ptr(dW), _lib.ptr(db), scratch.data_ptr(), nbytes,
-                  _stream())
-        ctx.grads = (dfeat, dW, db)
+                  dfeat.stride(0) if dfeat is not None else 0, _lib.ptr(dW), _lib.ptr(db), 1 if sunk else 0,
+                  scratch.data_ptr(), nbytes, _stream())
+        ctx.grads = (dfeat, None, None) if sunk else (dfeat, dW, db)
         ctx.unit_grad = unit_grad
         ctx.has_bias = b is not None
         return out
@@ -402,12 +477,17 @@ class HeadLoss(torch.autograd.Function):
         dfeat, dW, db = ctx.grads
         if not ctx.unit_grad:
             g = gout[0]
-            dfeat, dW, db = dfeat * g, dW * g, db * g
+            dfeat = dfeat * g
+            dW = dW * g if dW is not None else None
+            db = db * g if db is not None else None
         return dfeat, dW, (db if ctx.has_bias else None), None, None, None, None, None, None, None
 
 
-def head_loss(feat, linear, label, ids, nb, pix_w=None, rows=None, n_dev=None, unit_grad=False):
-    """(total_loss, total_acc) of a torch.nn.Linear head + the reference's SegmentationLoss on `feat`."""
+def head_loss(feat, linear, label, ids, nb, pix_w=None, rows=None, n_dev=None, unit_grad=False, full=False):
+    """(total_loss, total_acc) of a torch.nn.Linear head + the reference's SegmentationLoss on `feat`.
+    full=True returns the raw [4] tensor (loss, acc, bad sample ids, bad labels) instead."""
     rows = feat.shape[0] if rows is None else rows
     out = HeadLoss.apply(feat, linear.weight, linear.bias, label, ids, nb, pix_w, rows, n_dev, unit_grad)
+    if full:
+        return out
     return out[0], out[1].detach()

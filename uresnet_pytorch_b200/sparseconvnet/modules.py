@@ -71,6 +71,36 @@ class Identity(torch.nn.Module):
     def forward(self, x):
         return x
 
+
+class _Mark(torch.autograd.Function):
+    """Identity whose backward tells `config.backward_marks` that everything downstream of this point has run its
+    backward (used to start the gradient all-reduce of the inner U-Net levels while the outer level still runs)."""
+
+    @staticmethod
+    def forward(ctx, x, tag):
+        ctx.tag = tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = config.backward_mark_callback
+        if cb is not None:
+            cb(ctx.tag)
+        return g, None
+
+
+class MarkedSequential(Sequential):
+    """scn.Sequential that announces the end of its own backward pass (no parameters, same child names)."""
+
+    def __init__(self, tag):
+        super().__init__()
+        self._mark_tag = tag
+
+    def forward(self, x):
+        if config.backward_mark_callback is not None and torch.is_grad_enabled() and x.features.requires_grad:
+            x = x._like(_Mark.apply(x.features, self._mark_tag))
+        return super().forward(x)
+
     def input_spatial_size(self, out_size):
         return out_size
 
@@ -108,6 +138,7 @@ class InputLayer(torch.nn.Module):
         self.dimension = dimension
         self.spatial_size = _size_tuple(dimension, spatial_size)
         self.mode = mode
+        self.last_error_flag = None
 
     def forward(self, inp):
         coords, feats = inp[0], inp[1]
@@ -117,6 +148,9 @@ class InputLayer(torch.nn.Module):
             coords = coords.to(feats.device)
         md = Metadata(self.dimension)
         lv = md.set_input(coords, self.spatial_size)
+        # static regime: nothing is read back, so the out-of-range flag of this forward stays reachable for the
+        # owner of the step (Trainer folds it into its loss read-back)
+        self.last_error_flag = lv.n_dev[1:2] if md.static else None
         out = F.InputGather.apply(feats.float(), md, lv.rows, md.n_dev_ptr(lv))
         return SparseConvNetTensor(out, md, self.spatial_size)
 

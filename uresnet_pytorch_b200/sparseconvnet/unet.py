@@ -6,7 +6,7 @@ concat, `reps` more blocks (the first maps 2P -> P through a NetworkInNetwork sh
 Child indices are what scn produces, so state-dict keys match reference checkpoints.
 """
 from .modules import (AddTable, BatchNormLeakyReLU, ConcatTable, Convolution, Deconvolution, Identity, JoinTable,
-                      NetworkInNetwork, Sequential, SubmanifoldConvolution)
+                      MarkedSequential, NetworkInNetwork, Sequential, SubmanifoldConvolution)
 
 
 def _residual_block(dimension, a, b, leakiness):
@@ -34,16 +34,16 @@ def UNet(dimension, reps, nPlanes, residual_blocks=False, downsample=[2, 2], lea
         else:
             seq.add(_plain_block(dimension, a, b, leakiness))
 
-    def level(planes, n_in):
+    def level(planes, n_in, depth=0):
         seq = Sequential()
         width = planes[0]
         for r in range(reps):
             add_block(seq, n_in if (r == 0 and n_in != -1) else width, width)
         if len(planes) > 1:
-            inner = Sequential()
+            inner = MarkedSequential("unet.inner%d" % depth)  # a Sequential; tells a trainer when its backward ended
             inner.add(BatchNormLeakyReLU(width, leakiness=leakiness))
             inner.add(Convolution(dimension, width, planes[1], downsample[0], downsample[1], False))
-            inner.add(level(planes[1:], -1))
+            inner.add(level(planes[1:], -1, depth + 1))
             inner.add(BatchNormLeakyReLU(planes[1], leakiness=leakiness))
             inner.add(Deconvolution(dimension, planes[1], width, downsample[0], downsample[1], False))
             seq.add(ConcatTable().add(Identity()).add(inner))
