@@ -20,8 +20,8 @@ gradient and every BatchNorm running statistic with `OracleUResNet` run from the
 Tolerances are the fp32 ones of tests/test_gpu_mma.py (MATH_TF32X3 is fp32-equivalent):
 loss rel 1e-4, whole-gradient rel-L2 1e-3, running stats rel-L2 1e-4; per-tensor guard 5e-2 (the BatchNorm
 affine gradients of the deepest level nearly cancel: 2.0e-2 was measured for one of them at c3 with the
-whole-gradient error at 2.6e-4).  Measured on B200 (round 2): c2 whole-gradient 2e-4..4e-4, c3 2.6e-4, c5' 3e-4.
-The achieved numbers are printed (pytest -s / the captured output on failure).
+whole-gradient error at 2.6e-4).  The achieved numbers are printed (pytest -s / the captured output on failure);
+profiles/r2/ keeps the printed values of the round's runs.
 """
 import numpy as np
 import pytest
