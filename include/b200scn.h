@@ -175,6 +175,21 @@ int b200scn_wgrad_gpl(const float* A, int64_t lda, const float* B, int64_t ldb, 
                       int Ca, int Cb, float* dW, int accumulate, int math_mode, void* scratch, int64_t scratch_bytes,
                       void* stream);
 
+/* tcgen05 / TMEM variant of b200scn_conv_table for channel counts that are multiples of 16 (csrc/sparse_tc.cu):
+ * 128 output rows per CTA, contraction over (offset, input channel) in 32-wide blocks as tcgen05.mma kind::tf32,
+ * accumulator in TMEM, a missing table entry = a zero operand row.  Weights come PRE-PACKED (b200scn_pack_weights_tc,
+ * one launch for any number of layers: job = int64[12] {W, Wt, Wt_lo, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0, 0};
+ * Wt / Wt_lo = b200scn_conv_tc_packed_elems floats each: tf32 high parts and exact remainders, K-major); the
+ * offset flip and the transpose of a dgrad live in the packing strides.  res (optional, row stride ldr) is added to
+ * the result (residual connections of scn.UNet fused into the convolution).  math_mode TF32X3 or TF32.
+ * n_expect: rows the level typically holds when n_cap is only a buffer capacity (0 = unknown; launch heuristics). */
+int64_t b200scn_conv_tc_packed_elems(int K, int Cin, int Cout);
+int b200scn_conv_tc_supported(int K, int Cin, int Cout);
+int b200scn_pack_weights_tc(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, void* stream);
+int b200scn_conv_tc(const float* in, int64_t ldi, const float* Wt, const float* Wt_lo, const int32_t* table,
+                    int64_t ld_t, int K, int64_t n_cap, const int32_t* n_dev, int64_t n_expect, int Cin, int Cout,
+                    float* out, int64_t ldo, const float* res, int64_t ldr, int math_mode, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (iii) fused BatchNorm + (leaky) ReLU -- scn.BatchNormReLU (uresnet_sparse.py:23) and
  * scn.BatchNormLeakyReLU inside scn.UNet.  eps inside the sqrt, `retention` is scn's

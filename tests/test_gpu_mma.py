@@ -17,15 +17,16 @@ from test_gpu_layers import _check, _lift, _pair
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[0, 1 << 30], ids=["gpl", "pairs"])
+@pytest.fixture(autouse=True, params=[(True, 0), (False, 0), (False, 1 << 30)], ids=["tc", "gpl", "pairs"])
 def _conv_path(request):
-    """Run every test of this file through both tensor-core conv paths: grouped pair lists for all levels
-    (threshold 0) and in-kernel listing only (threshold huge)."""
+    """Run every test of this file through the three tensor-core conv paths: tcgen05 rule-table implicit GEMM
+    (sparse_tc.cu; the default), mma.sync over grouped pair lists for all levels (threshold 0) and mma.sync with
+    in-kernel listing only (threshold huge)."""
     from uresnet_pytorch_b200.sparseconvnet import config
-    prev = config.gpl_min_rows
-    config.gpl_min_rows = request.param
+    prev = config.gpl_min_rows, config.use_tc
+    config.use_tc, config.gpl_min_rows = request.param
     yield
-    config.gpl_min_rows = prev
+    config.gpl_min_rows, config.use_tc = prev
 
 TOL = {1: (3e-5, 2e-4), 2: (5e-3, 1e-2)}  # math mode -> (forward, gradient)
 
@@ -160,12 +161,13 @@ def test_gpl_and_pairs_kernels_agree(mode):
     conv = scn.SubmanifoldConvolution(3, 32, 48, 3, False).cuda()
     with torch.no_grad(), scn.math(mode):
         a = conv(x_g).features
-        scn.config.use_gpl = False
+        prev = scn.config.use_gpl, scn.config.use_tc
+        scn.config.use_gpl = scn.config.use_tc = False
         try:
             b = conv(x_g).features
         finally:
-            scn.config.use_gpl = True
-    assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
+            scn.config.use_gpl, scn.config.use_tc = prev
+    assert (a - b).abs().max().item() <= (1e-5 if mode == 1 else 2e-3) * a.abs().max().item()
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -209,3 +211,42 @@ print("ok", n)
     env = dict(os.environ, B200SCN_GPL_LARGE_MIN_ROWS="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (48, 80), (80, 48), (160, 96)])
+def test_conv_tc_residual_and_device_row_count(cin, cout):
+    """b200scn_conv_tc straight through the C-ABI: live row count from device memory below the buffer capacity
+    (rows beyond it neither read nor written), fused residual add, channel counts that are not multiples of 32,
+    output passes (Cout > 128 is covered by the c5 trainer test), against the FFMA neighbour-table kernel."""
+    from uresnet_pytorch_b200 import _lib
+    from uresnet_pytorch_b200.sparseconvnet import functional as F
+    from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+    data, _ = event_blob(3, 64, seed=17)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    md = Metadata(3)
+    size = (64, 64, 64)
+    lv = md.set_input(coords, size)
+    nbr = md.subm_table(size, 3)
+    n, K = lv.n, 27
+    cap = n + 300
+    torch.manual_seed(1)
+    x = torch.randn(cap, cin, device="cuda")
+    W = torch.nn.Parameter(torch.randn(K, cin, cout, device="cuda") * 0.1)
+    res = torch.randn(cap, cout, device="cuda")
+    table = torch.full((K, cap), -1, dtype=torch.int32, device="cuda")
+    table[:, :n] = nbr[:, :n]
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ref = torch.empty(n, cout, device="cuda")
+    _lib.call("b200scn_conv_table", x.data_ptr(), cin, W.data_ptr(), cin * cout, cout, 1, 0, nbr.data_ptr(),
+              nbr.stride(0), K, n, None, cin, cout, ref.data_ptr(), cout, 0, 0, st)
+    ent = F.packed_weights(W, W.detach(), cin, cout, cout, 1, 0, "tc")
+    hi = ent["buf"].data_ptr()
+    for mode, tol in ((1, 3e-5), (2, 5e-3)):
+        out = torch.full((cap, cout), 7.0, device="cuda")
+        _lib.call("b200scn_conv_tc", x.data_ptr(), cin, hi, hi + 4 * ent["elems"], table.data_ptr(), cap, K, cap,
+                  n_dev.data_ptr(), 0, cin, cout, out.data_ptr(), cout, res.data_ptr(), cout, mode, st)
+        torch.cuda.synchronize()
+        want = ref + res[:n]
+        assert (out[:n] - want).abs().max().item() <= tol * want.abs().max().item()
+        assert (out[n:] == 7.0).all()

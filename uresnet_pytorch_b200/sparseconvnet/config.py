@@ -14,6 +14,11 @@ static_shapes = False
 # before consuming parameter gradients.
 overlap_wgrad = False
 
+# True: forward / dgrad of SubmanifoldConvolution, Convolution and NetworkInNetwork run on the tcgen05 tensor cores as
+# a rule-table-driven implicit GEMM (csrc/sparse_tc.cu) whenever the channel counts are multiples of 16; False keeps
+# the mma.sync pair-list kernels for them (they still serve Deconvolution and every weight gradient)
+use_tc = not os.environ.get("B200SCN_NO_TC")
+
 # True: tensor-core convolutions read precomputed grouped pair lists (csrc/conv_gpl.cu) instead of
 # re-listing the rule pairs inside every launch (csrc/conv_pairs.cu)
 use_gpl = not os.environ.get("B200SCN_NO_GPL")

@@ -160,52 +160,88 @@ def _gpl_ok(gpl, x, Cin, Cout, math):
 # (FusedAdam writes through raw pointers, inside a CUDA graph) calls `repack_params` right after, which refreshes
 # every copy of the given parameters with ONE launch over a job table it returns -- the caller keeps that table
 # alive as long as a captured graph may replay the launch.
-def _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip):
+def _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip, kind="mma"):
+    """kind 'mma': fragment order of the mma.sync pair-list kernels (conv_gpl.cu); 'tc': K-major 32-channel blocks,
+    high and low tf32 parts, of the tcgen05 kernel (sparse_tc.cu)."""
     cache = getattr(W, "_b200_pack", None)
     if cache is None:
         cache = W._b200_pack = {}
-    key = (w_so == 1, kflip)
+    key = (kind, w_so == 1, kflip)
     ent = cache.get(key)
     if ent is None or ent["ptr"] != W3.data_ptr() or ent["shape"] != tuple(W3.shape):
         K = W3.shape[0]
-        buf = torch.empty(K * Cin * Cout, dtype=torch.float32, device=W3.device)
-        job = torch.tensor([W3.data_ptr(), buf.data_ptr(), K, Cin, Cout, W3.shape[1] * W3.shape[2], w_si, w_so, kflip,
-                            0], dtype=torch.int64).to(W3.device)
-        ent = dict(ptr=W3.data_ptr(), shape=tuple(W3.shape), buf=buf, job=job, version=None, elems=K * Cin * Cout)
+        if kind == "tc":
+            elems = int(_lib.load().b200scn_conv_tc_packed_elems(K, Cin, Cout))
+            buf = torch.empty(2 * elems, dtype=torch.float32, device=W3.device)  # [high | low]
+            job = torch.tensor([W3.data_ptr(), buf.data_ptr(), buf.data_ptr() + 4 * elems, K, Cin, Cout,
+                                W3.shape[1] * W3.shape[2], w_si, w_so, kflip, 0, 0], dtype=torch.int64).to(W3.device)
+        else:
+            elems = K * Cin * Cout
+            buf = torch.empty(elems, dtype=torch.float32, device=W3.device)
+            job = torch.tensor([W3.data_ptr(), buf.data_ptr(), K, Cin, Cout, W3.shape[1] * W3.shape[2], w_si, w_so,
+                                kflip, 0], dtype=torch.int64).to(W3.device)
+        ent = dict(ptr=W3.data_ptr(), shape=tuple(W3.shape), buf=buf, job=job, version=None, elems=elems, kind=kind)
         cache[key] = ent
     return ent
 
 
-def packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip):
-    """Device pointer of the fragment-ordered copy of W3 (a view of parameter W) for one direction."""
-    ent = _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip)
+_PACK_FN = {"mma": "b200scn_pack_weights", "tc": "b200scn_pack_weights_tc"}
+
+
+def packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip, kind="mma"):
+    """Cache entry of the packed copy of W3 (a view of parameter W) for one direction, refreshed if stale."""
+    ent = _pack_entry(W, W3, Cin, Cout, w_si, w_so, kflip, kind)
     if ent["version"] != W._version:
-        _lib.call("b200scn_pack_weights", ent["job"].data_ptr(), 1, ent["elems"], _stream())
+        _lib.call(_PACK_FN[kind], ent["job"].data_ptr(), 1, ent["elems"], _stream())
         ent["version"] = W._version
-    return ent["buf"].data_ptr()
+    return ent
 
 
 def repack_params(params, jobs=None):
-    """Refresh every cached copy of `params` with ONE launch.  Returns the job table (pass it back in to
-    reuse it; it is rebuilt only when the set of copies changed)."""
+    """Refresh every cached copy of `params` with ONE launch per kind.  Returns the job tables (pass them back
+    in to reuse them; they are rebuilt only when the set of copies changed)."""
     ents = [e for p in params for e in getattr(p, "_b200_pack", {}).values()]
     if not ents:
         return jobs
     ids = tuple(id(e) for e in ents)
     if jobs is None or jobs[0] != ids:
-        jobs = (ids, torch.cat([e["job"] for e in ents]), max(e["elems"] for e in ents), ents)
-    _lib.call("b200scn_pack_weights", jobs[1].data_ptr(), len(ents), jobs[2], _stream())
+        tabs = {}
+        for kind in _PACK_FN:
+            es = [e for e in ents if e["kind"] == kind]
+            if es:
+                tabs[kind] = (torch.cat([e["job"] for e in es]), len(es), max(e["elems"] for e in es))
+        jobs = (ids, tabs, ents)
+    for kind, (tab, n, mx) in jobs[1].items():
+        _lib.call(_PACK_FN[kind], tab.data_ptr(), n, mx, _stream())
     for p in params:
         for e in getattr(p, "_b200_pack", {}).values():
             e["version"] = p._version
     return jobs
 
 
+def _tc_ok(x, K, Cin, Cout, math):
+    """The tcgen05 rule-table kernel (csrc/sparse_tc.cu) takes this layer call."""
+    return (config.use_tc and math != 0 and K <= 27 and Cin % 16 == 0 and Cout % 16 == 0 and Cin >= 16 and Cout >= 16
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
+
+
+def _conv_tc(x, W, W3, w_si, w_so, kflip, table, n_out, n_out_dev, Cin, Cout, math, rows_hint=0, res=None):
+    """out[o] = (res[o] +) sum_k x[table[k][o]] @ W[k'] on the tcgen05 tensor cores (table None: identity, K = 1)."""
+    K = W3.shape[0]
+    ent = packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip, "tc")
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    hi = ent["buf"].data_ptr()
+    _lib.call("b200scn_conv_tc", x.data_ptr(), x.stride(0), hi, hi + 4 * ent["elems"], _lib.ptr(table),
+              table.stride(0) if table is not None else 0, K, n_out, n_out_dev, rows_hint, Cin, Cout, out.data_ptr(),
+              out.stride(0), _lib.ptr(res), res.stride(0) if res is not None else 0, math, _stream())
+    return out
+
+
 def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
     """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
-    Wp = packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip) if config.pack_weights else None
+    Wp = packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip)["buf"].data_ptr() if config.pack_weights else None
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
               kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
               n_out, n_out_dev, gpl.get("rows_hint", 0),
@@ -220,14 +256,17 @@ class TableConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, gpl_fwd=None,
-                gpl_bwd=None):
+                gpl_bwd=None, rows_hint=0):
         _check_cuda_f32(x, W)
         x = _rowmajor(x)
         W3 = W if W.dim() == 3 else W.unsqueeze(0)
         W3 = W3.contiguous()
         K, Cin, Cout = W3.shape
         math = config.math_mode
-        if _gpl_ok(gpl_fwd, x, Cin, Cout, math):
+        hint = gpl_fwd.get("rows_hint", 0) if gpl_fwd is not None else rows_hint
+        if _tc_ok(x, K, Cin, Cout, math):
+            out = _conv_tc(x, W, W3, Cout, 1, 0, table, n_out, n_out_dev, Cin, Cout, math, hint)
+        elif _gpl_ok(gpl_fwd, x, Cin, Cout, math):
             out = _conv_gpl(x, W, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math)
         else:
             out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
@@ -238,6 +277,7 @@ class TableConv(torch.autograd.Function):
         ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math, gpl_bwd)
         ctx.gpl_fwd = gpl_fwd
         ctx.w_param = W
+        ctx.rows_hint = hint
         return out
 
     @staticmethod
@@ -247,7 +287,10 @@ class TableConv(torch.autograd.Function):
         dout = _rowmajor(dout)
         K, Cin, Cout = W3.shape
         dx = dW = None
-        if ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
+        if ctx.needs_input_grad[0] and (table is None or symmetric) and _tc_ok(dout, K, Cout, Cin, math):
+            # dx[i] = sum_k dout[table[k][i]] @ W[K-1-k]^T   (the neighbour table is symmetric)
+            dx = _conv_tc(dout, ctx.w_param, W3, 1, Cout, 1, table, n_in, n_in_dev, Cout, Cin, math, ctx.rows_hint)
+        elif ctx.needs_input_grad[0] and _gpl_ok(gpl_bwd, dout, Cout, Cin, math):
             # same pair structure, transposed weights; the symmetric (submanifold) list needs the offset flip
             dx = _conv_gpl(dout, ctx.w_param, W3, 1, Cout, 1 if symmetric else 0, gpl_bwd, n_in, n_in_dev, Cout, Cin,
                            math)
@@ -266,7 +309,7 @@ class TableConv(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math, ctx.gpl_fwd, symmetric,
                         sink=_sink_view(ctx.w_param))
-        return dx, dW, None, None, None, None, None, None, None, None, None, None
+        return dx, dW, None, None, None, None, None, None, None, None, None, None, None
 
 
 class ParentConv(torch.autograd.Function):

@@ -218,7 +218,9 @@ class SubmanifoldConvolution(torch.nn.Module):
         if (config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0
                 and lv.rows >= config.gpl_min_rows):
             gpl = md.subm_gpl(x.spatial_size, self.filter_size)
-        out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None, gpl, gpl)
+        hint = config.gpl_rows_by_size.get(tuple(x.spatial_size), 0) if md.static else 0
+        out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None, gpl, gpl,
+                                int(hint))
         if self.bias is not None:
             out = out + self.bias
         return x._like(out)
@@ -276,8 +278,9 @@ class Convolution(torch.nn.Module):
         if (config.use_gpl and config.math_mode != 0 and self.nIn % 16 == 0 and self.nOut % 16 == 0
                 and nxt.rows >= config.gpl_min_rows):
             g_child, g_parent = md.strided_gpl(x.spatial_size, out_size, self.s)
+        hint = config.gpl_rows_by_size.get(tuple(out_size), 0) if md.static else 0
         out = F.TableConv.apply(x.features, self.weight, rules["child"], nxt.rows, md.n_dev_ptr(nxt), lv.rows,
-                                md.n_dev_ptr(lv), False, rules["parent"], rules["kofs"], g_child, g_parent)
+                                md.n_dev_ptr(lv), False, rules["parent"], rules["kofs"], g_child, g_parent, int(hint))
         if self.bias is not None:
             out = out + self.bias
         return x._like(out, out_size)
@@ -352,7 +355,9 @@ class NetworkInNetwork(torch.nn.Module):
         md = x.metadata
         lv = md.level(x.spatial_size)
         nd = md.n_dev_ptr(lv)
-        out = F.TableConv.apply(x.features, self.weight, None, lv.rows, nd, lv.rows, nd, True, None, None)
+        hint = config.gpl_rows_by_size.get(tuple(x.spatial_size), 0) if md.static else 0
+        out = F.TableConv.apply(x.features, self.weight, None, lv.rows, nd, lv.rows, nd, True, None, None, None, None,
+                                int(hint))
         if self.bias is not None:
             out = out + self.bias
         return x._like(out)
