@@ -268,7 +268,7 @@ def subm_roofline(args, math_mode):
         if use_gpl:  # what SubmanifoldConvolution.forward runs in the tensor-core math modes
             _lib.call("b200scn_conv_gpl", x.data_ptr(), C, W.data_ptr(), None, C * C, C, 1, 0, gpl["tile_rows"],
                       gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, C, C, out.data_ptr(), C, 0,
-                      math_mode, st.cuda_stream)
+                      None, 0, math_mode, st.cuda_stream)
         else:
             _lib.call("b200scn_conv_table", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, nbr.data_ptr(),
                       nbr.stride(0), K, n, None, C, C, out.data_ptr(), C, 0, math_mode, st.cuda_stream)

@@ -136,11 +136,12 @@ int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_s
  * tile_end == NULL: scanned lists (stage 0 + 1), else fixed-stride lists (stage 2);
  * n_out_expect: expected live row count when n_out_cap is a capacity (launch heuristics only; 0 = unknown) */
 /* Wp: optional fragment-ordered copy of W for this direction (b200scn_pack_weights with the same strides
- * and kflip), or NULL */
+ * and kflip), or NULL.  res (optional, row stride ldr): added to the result -- the shortcut of a residual block. */
 int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
                      int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
                      const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int64_t n_out_expect, int Cin,
-                     int Cout, float* out, int64_t ldo, int accumulate, int math_mode, void* stream);
+                     int Cout, float* out, int64_t ldo, int accumulate, const float* res, int64_t ldr, int math_mode,
+                     void* stream);
 
 /* Re-order weights into the mma fragment order b200scn_conv_gpl reads with coalesced 16-byte loads.
  * jobs_dev: device array of n_jobs records of int64[10] = {W ptr, out ptr, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0}
@@ -189,6 +190,16 @@ int b200scn_pack_weights_tc(const int64_t* jobs_dev, int n_jobs, int64_t max_ele
 int b200scn_conv_tc(const float* in, int64_t ldi, const float* Wt, const float* Wt_lo, const int32_t* table,
                     int64_t ld_t, int K, int64_t n_cap, const int32_t* n_dev, int64_t n_expect, int Cin, int Cout,
                     float* out, int64_t ldo, const float* res, int64_t ldr, int math_mode, void* stream);
+
+/* tcgen05 / TMEM weight gradient for the same layer shapes: dW[k][ci][co] (+)= sum_o in[table[k][o]][ci] dout[o][co]
+ * (gather on the input side: SubmanifoldConvolution, Convolution, NetworkInNetwork).  Per offset a GEMM that
+ * contracts over the rows, so both operands are MN-major tiles; the grid splits the flattened (offset, channel)
+ * axis into groups of 128 and the rows into splits whose partial blocks (scratch) are folded in fixed order.
+ * dW is contiguous [K][Cin][Cout].  n_expect as for b200scn_conv_tc; pass the same value to the scratch query. */
+int64_t b200scn_wgrad_tc_scratch_bytes(int64_t n_rows, int K, int Cin, int Cout);
+int b200scn_wgrad_tc(const float* in, int64_t ldi, const float* dout, int64_t ldd, const int32_t* table, int64_t ld_t,
+                     int K, int64_t n_cap, const int32_t* n_dev, int64_t n_expect, int Cin, int Cout, float* dW,
+                     int accumulate, int math_mode, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (iii) fused BatchNorm + (leaky) ReLU -- scn.BatchNormReLU (uresnet_sparse.py:23) and

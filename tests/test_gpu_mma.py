@@ -23,10 +23,11 @@ def _conv_path(request):
     (sparse_tc.cu; the default), mma.sync over grouped pair lists for all levels (threshold 0) and mma.sync with
     in-kernel listing only (threshold huge)."""
     from uresnet_pytorch_b200.sparseconvnet import config
-    prev = config.gpl_min_rows, config.use_tc
+    prev = config.gpl_min_rows, config.use_tc, config.tc_min_channels, config.tc_wgrad_min_channels
     config.use_tc, config.gpl_min_rows = request.param
+    config.tc_min_channels = config.tc_wgrad_min_channels = 16   # every width through the tcgen05 kernels in "tc"
     yield
-    config.gpl_min_rows, config.use_tc = prev
+    config.gpl_min_rows, config.use_tc, config.tc_min_channels, config.tc_wgrad_min_channels = prev
 
 TOL = {1: (3e-5, 2e-4), 2: (5e-3, 1e-2)}  # math mode -> (forward, gradient)
 
@@ -199,7 +200,8 @@ for (si, so, flip, ci, co) in ((Cout, 1, 0, Cin, Cout), (1, Cout, 1, Cout, Cin))
     xin = x if ci == Cin else torch.randn(n, ci, device="cuda")
     a = torch.empty(n, co, device="cuda"); b = torch.empty(n, co, device="cuda")
     _lib.call("b200scn_conv_gpl", xin.data_ptr(), ci, W.data_ptr(), None, Cin * Cout, si, so, flip, 128,
-              gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, ci, co, a.data_ptr(), co, 0, mode, st)
+              gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, ci, co, a.data_ptr(), co, 0, None, 0,
+              mode, st)
     _lib.call("b200scn_conv_table", xin.data_ptr(), ci, W.data_ptr(), Cin * Cout, si, so, flip, nbr.data_ptr(),
               nbr.stride(0), K, n, None, ci, co, b.data_ptr(), co, 0, 0, st)
     torch.cuda.synchronize()
@@ -242,7 +244,8 @@ def test_conv_tc_residual_and_device_row_count(cin, cout):
               nbr.stride(0), K, n, None, cin, cout, ref.data_ptr(), cout, 0, 0, st)
     ent = F.packed_weights(W, W.detach(), cin, cout, cout, 1, 0, "tc")
     hi = ent["buf"].data_ptr()
-    for mode, tol in ((1, 3e-5), (2, 5e-3)):
+    # 3xTF32 vs FFMA differ by summation order only: ~sqrt(27 cin) ulps of the largest partial sum
+    for mode, tol in ((1, 3e-5 if cin <= 80 else 6e-5), (2, 5e-3)):
         out = torch.full((cap, cout), 7.0, device="cuda")
         _lib.call("b200scn_conv_tc", x.data_ptr(), cin, hi, hi + 4 * ent["elems"], table.data_ptr(), cap, K, cap,
                   n_dev.data_ptr(), 0, cin, cout, out.data_ptr(), cout, res.data_ptr(), cout, mode, st)
@@ -250,3 +253,53 @@ def test_conv_tc_residual_and_device_row_count(cin, cout):
         want = ref + res[:n]
         assert (out[:n] - want).abs().max().item() <= tol * want.abs().max().item()
         assert (out[n:] == 7.0).all()
+
+
+@pytest.mark.parametrize("cin,cout,K", [(16, 16, 27), (32, 48, 27), (48, 80, 27), (80, 64, 27), (64, 32, 8), (32, 16, 1),
+                                        (96, 160, 27)])
+def test_wgrad_tc_matches_ffma_kernel(cin, cout, K):
+    """b200scn_wgrad_tc (tcgen05, MN-major operands, row splits folded in fixed order) through the C-ABI against
+    the FFMA table kernel: device-side row count below the capacity with garbage (NaN) beyond it, accumulation
+    into an existing buffer, submanifold (27), strided (8, child table) and NetworkInNetwork (1, no table) rules."""
+    from uresnet_pytorch_b200 import _lib
+    from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+    data, _ = event_blob(3, 64, seed=19)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    md = Metadata(3)
+    size = (64, 64, 64)
+    lv = md.set_input(coords, size)
+    L = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    if K == 27:
+        tab, n_out, n_in = md.subm_table(size, 3), lv.n, lv.n
+    elif K == 8:
+        rules = md.down_rules(size, (32, 32, 32), 2)
+        tab, n_out, n_in = rules["child"], md.level((32, 32, 32)).n, lv.n
+    else:
+        tab, n_out, n_in = None, lv.n, lv.n
+    cap = n_out + 200
+    torch.manual_seed(4)
+    x = torch.randn(n_in, cin, device="cuda")
+    dy = torch.full((cap, cout), float("nan"), device="cuda")
+    dy[:n_out] = torch.randn(n_out, cout, device="cuda")
+    table = None
+    if tab is not None:
+        table = torch.full((K, cap), -1, dtype=torch.int32, device="cuda")
+        table[:, :n_out] = tab[:, :n_out]
+    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
+    ref = torch.empty(K, cin, cout, device="cuda")
+    nb = L.b200scn_wgrad_scratch_bytes(n_out, K, cin, cout)
+    scr = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    _lib.call("b200scn_wgrad_table", x.data_ptr(), cin, dy.data_ptr(), cout, _lib.ptr(tab), tab.stride(0) if tab is not None else 0,
+              K, 0, n_out, None, cin, cout, ref.data_ptr(), 0, 0, scr.data_ptr(), nb, st)
+    for mode, tol in ((1, 5e-5), (2, 5e-3)):
+        for hint in (0, n_out):
+            nb2 = L.b200scn_wgrad_tc_scratch_bytes(hint if hint else cap, K, cin, cout)
+            scr2 = torch.empty(nb2, dtype=torch.uint8, device="cuda")
+            base = torch.randn(K, cin, cout, device="cuda")
+            dW = base.clone()
+            _lib.call("b200scn_wgrad_tc", x.data_ptr(), cin, dy.data_ptr(), cout, _lib.ptr(table), cap if table is not None else 0,
+                      K, cap, n_dev.data_ptr(), hint, cin, cout, dW.data_ptr(), 1, mode, scr2.data_ptr(), nb2, st)
+            torch.cuda.synchronize()
+            err = (dW - base - ref).abs().max().item() / ref.abs().max().item()
+            assert err <= tol, (mode, hint, err)

@@ -31,13 +31,16 @@ SIGNATURES = {
     "b200scn_wgrad_gpl": (_I32, [_P, _I64, _P, _I64, _I32, _P, _P, _I32, _I32, _I64, _P, _I64, _I32, _I32, _P, _I32,
                                  _I32, _P, _I64, _P]),
     "b200scn_conv_gpl": (_I32, [_P, _I64, _P, _P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _I32, _I64, _P, _I64, _I32,
-                                _I32, _P, _I64, _I32, _I32, _P]),
+                                _I32, _P, _I64, _I32, _P, _I64, _I32, _P]),
     "b200scn_pack_weights": (_I32, [_P, _I32, _I64, _P]),
     "b200scn_conv_tc_packed_elems": (_I64, [_I32, _I32, _I32]),
     "b200scn_conv_tc_supported": (_I32, [_I32, _I32, _I32]),
     "b200scn_pack_weights_tc": (_I32, [_P, _I32, _I64, _P]),
     "b200scn_conv_tc": (_I32, [_P, _I64, _P, _P, _P, _I64, _I32, _I64, _P, _I64, _I32, _I32, _P, _I64, _P, _I64, _I32,
                                _P]),
+    "b200scn_wgrad_tc_scratch_bytes": (_I64, [_I64, _I32, _I32, _I32]),
+    "b200scn_wgrad_tc": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _I64, _P, _I64, _I32, _I32, _P, _I32, _I32, _P,
+                                _I64, _P]),
     "b200scn_dense_conv_tc_scratch_bytes": (_I64, [_I32, _I32, _I32]),
     "b200scn_dense_conv_tc": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _I32, _P, _I64,
                                      _P]),

@@ -50,27 +50,12 @@ int conv_parent_simt(const float*, int64_t, const float*, int64_t, int64_t, int6
 int64_t wgrad_scratch_bytes_simt(int64_t, int, int, int);
 int wgrad_table_simt(const float*, int64_t, const float*, int64_t, const int32_t*, int64_t, int, int, int64_t,
                      const int32_t*, int, int, float*, int, void*, int64_t, cudaStream_t, const DenseGeom&);
-// conv_mma.cu
-bool conv_mma_supported(int Cin, int Cout, int K, int64_t ldi, const void* in);
-int conv_rows_mma(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t,
-                  const int32_t*, const uint8_t*, int, int64_t, const int32_t*, int, int, float*, int64_t, int, int,
-                  cudaStream_t);
-
 // conv_pairs.cu
 bool conv_pairs_supported(int Cin, int Cout, int K, int64_t ldi, const void* in, int64_t n_cap, int64_t ld,
                           int64_t ldo, int64_t n_in_max);
 int conv_rows_pairs(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, const int32_t*, int64_t,
                     const int32_t*, const uint8_t*, int, int64_t, const int32_t*, int, int, float*, int64_t, int, int,
                     cudaStream_t);
-// which tensor-core forward kernel serves the non-FP32 math modes: 0 = dense pairs (default), 1 = conv_mma
-static int conv_impl() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200SCN_CONV_IMPL");
-    v = (e != nullptr && e[0] == 'm') ? 1 : 0;
-  }
-  return v;
-}
 // wgrad_mma.cu
 bool wgrad_mma_supported(int64_t, int, int, int, int64_t, int64_t, const void*, const void*);
 int64_t wgrad_scratch_bytes_mma(int64_t, int, int, int);
@@ -102,13 +87,9 @@ extern "C" int b200scn_conv_table(const float* in, int64_t ldi, const float* W, 
   B200_CHECK_ARG(table == nullptr || ld >= n_out_cap, "conv_table: ld < n_out_cap");
   B200_CHECK_ARG(ldi >= Cin && ldo >= Cout, "conv_table: row stride smaller than channel count");
   B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "conv_table: bad math mode %d", math_mode);
-  if (math_mode != B200SCN_MATH_FP32 && conv_impl() == 0 &&
-      conv_pairs_supported(Cin, Cout, K, ldi, in, n_out_cap, ld, ldo, 1ll << 26))
+  if (math_mode != B200SCN_MATH_FP32 && conv_pairs_supported(Cin, Cout, K, ldi, in, n_out_cap, ld, ldo, 1ll << 26))
     return conv_rows_pairs(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, nullptr, nullptr, K, n_out_cap, n_out_dev,
                            Cin, Cout, out, ldo, accumulate, math_mode, (cudaStream_t)stream);
-  if (math_mode != B200SCN_MATH_FP32 && conv_mma_supported(Cin, Cout, K, ldi, in))
-    return conv_rows_mma(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, nullptr, nullptr, K, n_out_cap, n_out_dev,
-                         Cin, Cout, out, ldo, accumulate, math_mode, (cudaStream_t)stream);
   return conv_table_simt(in, ldi, W, w_sk, w_si, w_so, kflip, table, ld, K, n_out_cap, n_out_dev, Cin, Cout, out, ldo,
                          accumulate, (cudaStream_t)stream);
 }
@@ -121,13 +102,9 @@ extern "C" int b200scn_conv_parent(const float* in, int64_t ldi, const float* W,
   B200_CHECK_ARG(parent != nullptr && kofs != nullptr, "conv_parent: parent/kofs must not be NULL");
   B200_CHECK_ARG(ldi >= Cin && ldo >= Cout, "conv_parent: row stride smaller than channel count");
   B200_CHECK_ARG(math_mode >= 0 && math_mode <= 2, "conv_parent: bad math mode %d", math_mode);
-  if (math_mode != B200SCN_MATH_FP32 && conv_impl() == 0 &&
-      conv_pairs_supported(Cin, Cout, K, ldi, in, n_out_cap, 0, ldo, 1ll << 26))
+  if (math_mode != B200SCN_MATH_FP32 && conv_pairs_supported(Cin, Cout, K, ldi, in, n_out_cap, 0, ldo, 1ll << 26))
     return conv_rows_pairs(in, ldi, W, w_sk, w_si, w_so, 0, nullptr, 0, parent, kofs, K, n_out_cap, n_out_dev, Cin,
                            Cout, out, ldo, 0, math_mode, (cudaStream_t)stream);
-  if (math_mode != B200SCN_MATH_FP32 && conv_mma_supported(Cin, Cout, K, ldi, in))
-    return conv_rows_mma(in, ldi, W, w_sk, w_si, w_so, 0, nullptr, 0, parent, kofs, K, n_out_cap, n_out_dev, Cin, Cout,
-                         out, ldo, 0, math_mode, (cudaStream_t)stream);
   return conv_parent_simt(in, ldi, W, w_sk, w_si, w_so, parent, kofs, K, n_out_cap, n_out_dev, Cin, Cout, out, ldo,
                           (cudaStream_t)stream);
 }

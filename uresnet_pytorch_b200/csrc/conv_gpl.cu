@@ -151,6 +151,7 @@ struct GplParams {
   int K;
   int64_t n_cap; const int32_t* n_dev;
   float* out; int ldo; int accumulate;
+  const float* res; int ldr;  // optional residual added to the result (shortcut of a residual block)
   int warps, split;  // split != 0: the CTA's warps share one tile
   uint32_t ones;     // 0xffffffff (opaque to the compiler)
 };
@@ -455,6 +456,10 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
           v = acc[src];
         }
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
+        if (p.res != nullptr) {
+          const float* rr = p.res + (int64_t)(base + row) * p.ldr + cob + 4 * c4;
+          v.x += __ldg(rr); v.y += __ldg(rr + 1); v.z += __ldg(rr + 2); v.w += __ldg(rr + 3);
+        }
         if (vec_ok) {
           if (p.accumulate) {
             const float4 old = *reinterpret_cast<const float4*>(o);
@@ -640,6 +645,10 @@ __global__ void __launch_bounds__(512, MT == 1 ? 2 : 1) k_conv_gpl_small(const G
           v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
         }
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
+        if (p.res != nullptr) {
+          const float* rr = p.res + (int64_t)(base + row) * p.ldr + cob + 4 * c4;
+          v.x += __ldg(rr); v.y += __ldg(rr + 1); v.z += __ldg(rr + 2); v.w += __ldg(rr + 3);
+        }
         if (vec_ok) {
           if (p.accumulate) {
             const float4 old = *reinterpret_cast<const float4*>(o);
@@ -898,7 +907,7 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
                                 int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
                                 const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev,
                                 int64_t n_out_expect, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
-                                int math_mode, void* stream) {
+                                const float* res, int64_t ldr, int math_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16, "conv_gpl: channels must be multiples of 16");
   B200_CHECK_ARG(math_mode == B200SCN_MATH_TF32 || math_mode == B200SCN_MATH_TF32X3, "conv_gpl: tensor-core math modes only");
@@ -914,6 +923,7 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   p.in = in; p.ldi = (int)ldi; p.W = W; p.w_sk = (int)w_sk; p.w_si = (int)w_si; p.w_so = (int)w_so; p.kflip = kflip;
   p.tile_off = tile_off; p.tile_end = tile_end; p.g_rec = reinterpret_cast<const int4*>(g_rec); p.Q = Cin / 16;
   p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = accumulate;
+  p.res = res; p.ldr = (int)ldr;
   p.warps = 8; p.split = 1; p.ones = 0xffffffffu;
 
   // large inputs (enough 128-row tiles to give every SM a CTA of one-tile warps) with scanned lists and

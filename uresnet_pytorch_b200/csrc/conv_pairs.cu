@@ -1,7 +1,7 @@
 // Gather-GEMM sparse convolution, "dense pairs" formulation (forward / dgrad of
 // SubmanifoldConvolution, Convolution, Deconvolution, NetworkInNetwork) on the tensor pipe.
 //
-// conv_mma.cu keeps output rows in registers and pays an MMA for every (offset, 8-site tile)
+// An output-stationary mma.sync kernel (round 1, removed) paid an MMA for every (offset, 8-site tile)
 // that has at least one neighbour -- at the fine U-Net levels only ~2.4 of the 8 columns of
 // such an MMA carry data and the bookkeeping around it dominates the issue slots (ncu:
 // profiles/README.md).  Here each warp owns R = 32*NCH consecutive output rows and, for every

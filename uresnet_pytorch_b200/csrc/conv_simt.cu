@@ -1,7 +1,7 @@
 // Gather-GEMM sparse convolutions, exact-fp32 (FFMA) kernels: forward/dgrad (table and
 // parent forms) and wgrad (north-star job 2).  These are the MATH_FP32 path and the
-// any-channel-count path; conv_mma.cu holds the tensor-core kernels for channel counts that
-// are multiples of 16/8.
+// any-channel-count path; sparse_tc.cu (tcgen05) and conv_gpl.cu / conv_pairs.cu (mma.sync) hold the tensor-core
+// kernels for channel counts that are multiples of 16.
 //
 // Output-stationary formulation: every CTA owns a tile of output rows, walks the kernel
 // offsets k = 0..K-1 in order, gathers the input rows named by table[k][row] into shared

@@ -18,6 +18,15 @@ overlap_wgrad = False
 # a rule-table-driven implicit GEMM (csrc/sparse_tc.cu) whenever the channel counts are multiples of 16; False keeps
 # the mma.sync pair-list kernels for them (they still serve Deconvolution and every weight gradient)
 use_tc = not os.environ.get("B200SCN_NO_TC")
+# narrowest layer (min(nIn, nOut)) the tcgen05 kernels take; below it the mma.sync pair-list kernels are faster
+tc_min_channels = int(os.environ.get("B200SCN_TC_MIN_C", "96"))
+tc_wgrad_min_channels = int(os.environ.get("B200SCN_TC_WGRAD_MIN_C", "96"))
+# True: their weight gradients too (k_sparse_wgrad_tc); False: mma.sync over the forward pair lists (wgrad_gpl.cu)
+use_tc_wgrad = not os.environ.get("B200SCN_NO_TC_WGRAD")
+
+# True: ConcatTable(shortcut | ... SubmanifoldConvolution) + AddTable -- the residual blocks of scn.UNet -- form their
+# sum inside the last convolution's epilogue instead of a separate elementwise pass
+fuse_residual = not os.environ.get("B200SCN_NO_FUSE_RES")
 
 # True: tensor-core convolutions read precomputed grouped pair lists (csrc/conv_gpl.cu) instead of
 # re-listing the rule pairs inside every launch (csrc/conv_pairs.cu)

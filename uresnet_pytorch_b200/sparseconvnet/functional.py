@@ -108,16 +108,26 @@ def _sink_view(param):
     return None
 
 
-def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=False, sink=None):
+def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=False, sink=None, rows_hint=0):
     """dW [K, Ca, Cb].  `gpl`: the layer's FORWARD pair list (its out rows index B) -- when given, and the
     shapes allow, the weight gradient walks it (csrc/wgrad_gpl.cu) instead of re-compacting the table.
     `sink`: accumulate into this preallocated view (GradSink) and return None."""
     Ca, Cb = A.shape[1], B.shape[1]
     L = _lib.load()
-    use_gpl = (gpl is not None and gpl.get("koff") is not None and config.use_gpl and config.wgrad_gpl and math != 0
-               and Ca % 16 == 0 and Cb % 16 == 0 and A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0
+    aligned = (Ca % 16 == 0 and Cb % 16 == 0 and A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0
                and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
-    nbytes = L.b200scn_wgrad_gpl_scratch_bytes(K, Ca, Cb) if use_gpl else L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
+    # tcgen05 kernel (sparse_tc.cu): rule tables that gather on the A side (subm, strided conv, NiN)
+    use_tc = (config.use_tc and config.use_tc_wgrad and math != 0 and aligned and gather_b == 0 and K <= 27
+              and (table is not None or K == 1) and min(Ca, Cb) >= max(config.tc_wgrad_min_channels, 16))
+    use_gpl = (not use_tc and gpl is not None and gpl.get("koff") is not None and config.use_gpl and config.wgrad_gpl
+               and math != 0 and aligned)
+    hint = rows_hint if 0 < rows_hint < rows else rows
+    if use_tc:
+        nbytes = L.b200scn_wgrad_tc_scratch_bytes(hint, K, Ca, Cb)
+    elif use_gpl:
+        nbytes = L.b200scn_wgrad_gpl_scratch_bytes(K, Ca, Cb)
+    else:
+        nbytes = L.b200scn_wgrad_scratch_bytes(rows, K, Ca, Cb)
 
     # every buffer is allocated on the main stream; only the kernels move to the side stream
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
@@ -125,6 +135,11 @@ def _wgrad(A, B, table, K, gather_b, rows, n_dev, w_shape, math, gpl=None, subm=
     acc = 1 if sink is not None else 0
 
     def run():
+        if use_tc:
+            _lib.call("b200scn_wgrad_tc", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _lib.ptr(table),
+                      table.stride(0) if table is not None else 0, K, rows, n_dev, hint, Ca, Cb, dW.data_ptr(), acc,
+                      math, scratch.data_ptr(), nbytes, _stream())
+            return
         if use_gpl:
             _lib.call("b200scn_wgrad_gpl", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), gpl["tile_rows"],
                       gpl["g_rec"].data_ptr(), gpl["koff"].data_ptr(), K, int(subm), rows, n_dev,
@@ -220,8 +235,11 @@ def repack_params(params, jobs=None):
 
 
 def _tc_ok(x, K, Cin, Cout, math):
-    """The tcgen05 rule-table kernel (csrc/sparse_tc.cu) takes this layer call."""
-    return (config.use_tc and math != 0 and K <= 27 and Cin % 16 == 0 and Cout % 16 == 0 and Cin >= 16 and Cout >= 16
+    """The tcgen05 rule-table kernel (csrc/sparse_tc.cu) takes this layer call.  It wins where the layer is wide
+    (config.tc_min_channels: measured cross-over, profiles/README.md round 2): each 128-row operand tile is read
+    by the tensor core once per 8 contraction elements whatever N is, so narrow layers are shared-memory bound."""
+    return (config.use_tc and math != 0 and K <= 27 and Cin % 16 == 0 and Cout % 16 == 0
+            and min(Cin, Cout) >= max(config.tc_min_channels, 16)
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0)
 
 
@@ -237,7 +255,7 @@ def _conv_tc(x, W, W3, w_si, w_so, kflip, table, n_out, n_out_dev, Cin, Cout, ma
     return out
 
 
-def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math):
+def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, math, res=None):
     """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
@@ -245,7 +263,8 @@ def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, mat
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
               kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
               n_out, n_out_dev, gpl.get("rows_hint", 0),
-              Cin, Cout, out.data_ptr(), out.stride(0), 0, math, _stream())
+              Cin, Cout, out.data_ptr(), out.stride(0), 0, _lib.ptr(res), res.stride(0) if res is not None else 0, math,
+              _stream())
     return out
 
 
@@ -256,7 +275,9 @@ class TableConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, gpl_fwd=None,
-                gpl_bwd=None, rows_hint=0):
+                gpl_bwd=None, rows_hint=0, res=None):
+        """res: optional [n_out, Cout] tensor added to the result (the shortcut of a residual block, fused into
+        the convolution's epilogue on the tcgen05 path)."""
         _check_cuda_f32(x, W)
         x = _rowmajor(x)
         W3 = W if W.dim() == 3 else W.unsqueeze(0)
@@ -264,15 +285,23 @@ class TableConv(torch.autograd.Function):
         K, Cin, Cout = W3.shape
         math = config.math_mode
         hint = gpl_fwd.get("rows_hint", 0) if gpl_fwd is not None else rows_hint
+        if res is not None:
+            res = _rowmajor(res)
+        fused_res = False
         if _tc_ok(x, K, Cin, Cout, math):
-            out = _conv_tc(x, W, W3, Cout, 1, 0, table, n_out, n_out_dev, Cin, Cout, math, hint)
+            fused_res = res is not None and res.stride(0) % 4 == 0 and res.data_ptr() % 16 == 0
+            out = _conv_tc(x, W, W3, Cout, 1, 0, table, n_out, n_out_dev, Cin, Cout, math, hint,
+                           res if fused_res else None)
         elif _gpl_ok(gpl_fwd, x, Cin, Cout, math):
-            out = _conv_gpl(x, W, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math)
+            fused_res = res is not None
+            out = _conv_gpl(x, W, W3, Cout, 1, 0, gpl_fwd, n_out, n_out_dev, Cin, Cout, math, res)
         else:
             out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
             _lib.call("b200scn_conv_table", x.data_ptr(), x.stride(0), W3.data_ptr(), Cin * Cout, Cout, 1, 0,
                       _lib.ptr(table), table.stride(0) if table is not None else 0, K, n_out, n_out_dev, Cin, Cout,
                       out.data_ptr(), out.stride(0), 0, math, _stream())
+        if res is not None and not fused_res:
+            out = out + res[:n_out]
         ctx.save_for_backward(x, W3)
         ctx.misc = (table, n_out, n_out_dev, n_in, n_in_dev, symmetric, parent, kofs, W.shape, math, gpl_bwd)
         ctx.gpl_fwd = gpl_fwd
@@ -308,8 +337,9 @@ class TableConv(torch.autograd.Function):
                           dx.stride(0), math, _stream())
         if ctx.needs_input_grad[1]:
             dW = _wgrad(x, dout, table, K, 0, n_out, n_out_dev, w_shape, math, ctx.gpl_fwd, symmetric,
-                        sink=_sink_view(ctx.w_param))
-        return dx, dW, None, None, None, None, None, None, None, None, None, None, None
+                        sink=_sink_view(ctx.w_param), rows_hint=ctx.rows_hint)
+        d_res = dout if (len(ctx.needs_input_grad) > 13 and ctx.needs_input_grad[13]) else None
+        return dx, dW, None, None, None, None, None, None, None, None, None, None, None, d_res
 
 
 class ParentConv(torch.autograd.Function):

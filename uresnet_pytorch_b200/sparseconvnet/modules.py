@@ -55,13 +55,35 @@ class Sequential(torch.nn.Sequential):
         return out_size
 
 
+class _FusedSum(list):
+    """[shortcut, body] of a residual block whose sum was already formed inside the body's last convolution."""
+    fused = None
+
+
 class ConcatTable(torch.nn.Module):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
         return self
 
     def forward(self, x):
-        return [m(x) for m in self._modules.values()]
+        mods = list(self._modules.values())
+        # residual block of scn.UNet (shortcut | BN-conv-BN-conv) followed by AddTable: hand the shortcut to the last
+        # convolution, which adds it in its epilogue -- the AddTable after it then has nothing left to do
+        if (config.fuse_residual and len(mods) == 2 and isinstance(mods[0], (Identity, NetworkInNetwork))
+                and isinstance(mods[1], Sequential) and len(mods[1]) > 0
+                and isinstance(list(mods[1]._modules.values())[-1], SubmanifoldConvolution)
+                and list(mods[1]._modules.values())[-1].bias is None):
+            s = mods[0](x)
+            body = list(mods[1]._modules.values())
+            y = x
+            for m in body[:-1]:
+                y = m(y)
+            if tuple(y.spatial_size) == tuple(s.spatial_size) and s.features.shape[1] == body[-1].nOut:
+                out = _FusedSum([s, None])
+                out.fused = body[-1](y, res=s.features)
+                return out
+            return [s, body[-1](y)]
+        return [m(x) for m in mods]
 
     def input_spatial_size(self, out_size):
         return list(self._modules.values())[0].input_spatial_size(out_size) if len(self._modules) else out_size
@@ -107,6 +129,8 @@ class MarkedSequential(Sequential):
 
 class AddTable(torch.nn.Module):
     def forward(self, xs):
+        if getattr(xs, "fused", None) is not None:
+            return xs.fused
         feats = xs[0].features
         for x in xs[1:]:
             feats = feats + x.features
@@ -206,7 +230,7 @@ class SubmanifoldConvolution(torch.nn.Module):
         _load_compat(self, state_dict, prefix)
         super()._load_from_state_dict(state_dict, prefix, *args, **kw)
 
-    def forward(self, x):
+    def forward(self, x, res=None):
         if x.features.shape[1] != self.nIn:
             raise AssertionError("SubmanifoldConvolution: expected %d input planes, got %d"
                                  % (self.nIn, x.features.shape[1]))
@@ -220,7 +244,7 @@ class SubmanifoldConvolution(torch.nn.Module):
             gpl = md.subm_gpl(x.spatial_size, self.filter_size)
         hint = config.gpl_rows_by_size.get(tuple(x.spatial_size), 0) if md.static else 0
         out = F.TableConv.apply(x.features, self.weight, nbr, lv.rows, nd, lv.rows, nd, True, None, None, gpl, gpl,
-                                int(hint))
+                                int(hint), res)
         if self.bias is not None:
             out = out + self.bias
         return x._like(out)
