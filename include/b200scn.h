@@ -263,10 +263,6 @@ int b200scn_segsum_rows(const float* src, int64_t lds, const int32_t* first_idx,
 /* ---------------------------------------------------------------------------------------
  * (v) elementwise helpers used by the table modules (AddTable / JoinTable) and the trainer.
  * ------------------------------------------------------------------------------------- */
-/* out[r, 0:C] = a[r, 0:C] + b[r, 0:C] */
-int b200scn_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n_cap,
-                     const int32_t* n_dev, int C, float* out, int64_t ldo, void* stream);
-
 /* ---------------------------------------------------------------------------------------
  * (vi) dense path -- the Conv{2,3}d / ConvTranspose{2,3}d / replicate-pad family of
  * /root/reference/uresnet/models/uresnet_dense.py:12-226 on channels-last [B, (D,) H, W, C] fp32.

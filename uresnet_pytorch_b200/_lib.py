@@ -71,7 +71,6 @@ SIGNATURES = {
     "b200scn_collate": (_I32, [_P, _I64, _P, _I32, _I32, _I32, _I64, _P, _I64, _P, _P]),
     "b200scn_gather_rows": (_I32, [_P, _I64, _P, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_segsum_rows": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P]),
-    "b200scn_add_rows": (_I32, [_P, _I64, _P, _I64, _I64, _P, _I32, _P, _I64, _P]),
     "b200scn_dense_conv": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "b200scn_dense_wgrad_scratch_bytes": (_I64, [_P, _I32, _I32, _I32]),
     "b200scn_dense_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I64, _P]),

@@ -1,6 +1,6 @@
 // Input / output layer feature movement (scn.InputLayer mode-3 sums and scn.OutputLayer,
-// /root/reference/uresnet/models/uresnet_sparse.py:20,24) and the row-wise add used by
-// AddTable.  Pure HBM-bound row copies: one thread per (row, column), consecutive threads on
+// /root/reference/uresnet/models/uresnet_sparse.py:20,24) and batch collation.  Pure HBM-bound row copies:
+// one thread per (row, column), consecutive threads on
 // consecutive columns.
 #include "common.cuh"
 
@@ -31,18 +31,6 @@ __global__ void k_segsum_rows(const float* __restrict__ src, int64_t lds, const 
     const int b = __ldg(seg_off + r), en = __ldg(seg_off + r + 1);
     for (int j = b; j < en; ++j) v += __ldg(src + (int64_t)__ldg(seg + j) * lds + c);
     dst[r * ldd + c] = v;
-  }
-}
-
-__global__ void k_add_rows(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
-                           int64_t n_cap, const int32_t* __restrict__ n_dev, int C, float* __restrict__ out,
-                           int64_t ldo) {
-  const int64_t n = live_rows(n_dev, n_cap);
-  const int64_t total = n * C;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e / C;
-    const int c = (int)(e - r * C);
-    out[r * ldo + c] = __ldg(a + r * lda + c) + __ldg(b + r * ldb + c);
   }
 }
 
@@ -97,16 +85,6 @@ extern "C" int b200scn_segsum_rows(const float* src, int64_t lds, const int32_t*
                                                                       C, dst, ldd);
   count_launches(1);
   B200_CHECK_LAUNCH("segsum_rows");
-  return 0;
-}
-
-extern "C" int b200scn_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n_cap,
-                                const int32_t* n_dev, int C, float* out, int64_t ldo, void* stream) {
-  B200_CHECK_ARG(C >= 1, "add_rows: C must be >= 1");
-  if (n_cap == 0) return 0;
-  k_add_rows<<<ew_grid(n_cap * C), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n_cap, n_dev, C, out, ldo);
-  count_launches(1);
-  B200_CHECK_LAUNCH("add_rows");
   return 0;
 }
 

@@ -601,6 +601,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_sparse_wgrad_tc(const SwtParams
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                      : "r"(t_row + (uint32_t)c));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (X3) {  // columns [N, 2N): the A_hi x B_lo sums
+          uint32_t w[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                       : "r"(t_row + (uint32_t)(N + c)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0u;
@@ -615,6 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sparse_wgrad_tc(const SwtParams
     // ===== MMA issuer: D[128 x N] += A^T B over the 32 rows of every stage; both operands MN-major =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_wide = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     for (int it = 0; it < n_it; ++it) {
       const int s = it % S;
       mbar_wait(&full_bar[s], (it / S) & 1);
@@ -625,9 +636,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_sparse_wgrad_tc(const SwtParams
         const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
         const uint32_t ko = ks * 1024;  // 8 rows of 128 bytes
         if (X3) {
-          umma_tf32(tmem_base, umma_desc_mn(a_addr + a_lo_off + ko, tile_bytes, 512), umma_desc_mn(b_addr + ko, tile_bytes, 512), idesc, acc);
-          umma_tf32(tmem_base, umma_desc_mn(a_addr + ko, tile_bytes, 512), umma_desc_mn(a_addr + b_lo_off + ko, tile_bytes, 512), idesc, 1u);
-          umma_tf32(tmem_base, umma_desc_mn(a_addr + ko, tile_bytes, 512), umma_desc_mn(b_addr + ko, tile_bytes, 512), idesc, 1u);
+          // two MMAs per k-step (see k_sparse_conv_tc): A_hi x [B_hi | B_lo] as one instruction of width 2N --
+          // the low dout tiles follow the high ones in shared memory -- then A_lo x B_hi into columns [0, N)
+          umma_tf32(tmem_base, umma_desc_mn(a_addr + ko, tile_bytes, 512), umma_desc_mn(b_addr + ko, tile_bytes, 512), idesc_wide, acc);
+          umma_tf32(tmem_base, umma_desc_mn(a_addr + a_lo_off + ko, tile_bytes, 512), umma_desc_mn(b_addr + ko, tile_bytes, 512), idesc, 1u);
         } else {
           umma_tf32(tmem_base, umma_desc_mn(a_addr + ko, tile_bytes, 512), umma_desc_mn(b_addr + ko, tile_bytes, 512), idesc, acc);
         }
@@ -717,7 +729,7 @@ extern "C" int b200scn_wgrad_tc(const float* in, int64_t ldi, const float* dout,
   p.Cin = Cin; p.Cout = Cout; p.n_pass = n_pass; p.N = (n_pass + 31) / 32 * 32;
   p.part = reinterpret_cast<float*>(scratch); p.part_stride = elems;
   uint32_t cols = 32;
-  while ((int)cols < p.N) cols <<= 1;
+  while ((int)cols < p.N * (x3 ? 2 : 1)) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage = (size_t)(4 + p.N / 32) * kWR * 128 * (x3 ? 2 : 1);
   const int n_mg = (K * (Cin / 16) + 7) / 8;
