@@ -263,12 +263,16 @@ def subm_roofline(args, math_mode):
 
     use_gpl = scn.config.use_gpl and math_mode != scn.MATH_FP32 and not os.environ.get("B200SCN_NO_GPL")
     gpl = md.subm_gpl(size, 3) if use_gpl else None
+    if use_gpl:  # the list layout SubmanifoldConvolution.forward would pick for this shape (functional._conv_gpl)
+        want = _lib.load().b200scn_conv_gpl_layout(gpl["tile_rows"], int(gpl["tile_end"] is None), n, C, C, K, 1, math_mode)
+        if want:
+            gpl = md.subm_gpl(size, 3, want)
 
     def launch():
         if use_gpl:  # what SubmanifoldConvolution.forward runs in the tensor-core math modes
             _lib.call("b200scn_conv_gpl", x.data_ptr(), C, W.data_ptr(), None, C * C, C, 1, 0, gpl["tile_rows"],
-                      gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, C, C, out.data_ptr(), C, 0,
-                      None, 0, math_mode, st.cuda_stream)
+                      gpl["layout"], gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, C, C,
+                      out.data_ptr(), C, 0, None, 0, math_mode, st.cuda_stream)
         else:
             _lib.call("b200scn_conv_table", x.data_ptr(), C, W.data_ptr(), C * C, C, 1, 0, nbr.data_ptr(),
                       nbr.stride(0), K, n, None, C, C, out.data_ptr(), C, 0, math_mode, st.cuda_stream)
@@ -300,7 +304,8 @@ def subm_roofline(args, math_mode):
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "kernel": ("b200scn_conv_gpl" if use_gpl else "b200scn_conv_table") + " (subm 3^3, 16->16, fwd)",
             "workload": "%d events of 512^3 concatenated: %d active sites, %d rule pairs (working set > L2)"
                         % (args.roofline_events, n, pairs),
-            "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3, "gflops": 2.0 * pairs * C * C / t / 1e9}
+            "algorithmic_bytes_per_launch": alg, "launch_ms": t * 1e3, "gflops": 2.0 * pairs * C * C / t / 1e9,
+            "pair_list_layout": gpl["layout"] if use_gpl else None}
 
 
 def cpu_baseline_subprocess(args):

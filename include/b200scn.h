@@ -110,14 +110,21 @@ int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_de
  * stage 2 -> single pass, fixed-stride slots: tile_off[tiles] = begin, tile_end[tiles] = end of every tile,
  *            cap_groups >= b200scn_gpl_max_groups(); no scan and no read-back (CUDA-graph regime).
  * koff (optional, stages 1 and 2): int32[tiles * (K + 1)], first group of every offset inside each tile
- * (entry K = end of the tile) -- the index b200scn_wgrad_gpl walks. */
+ * (entry K = end of the tile) -- the index b200scn_wgrad_gpl walks.
+ * layout: 0 = every offset's pairs compacted into groups, offsets ascending (what every kernel reads).
+ *         1 / 3 = dense-first, submanifold tables only, no koff: the centre offset (1), or the centre and its two
+ *         neighbours along the last axis (3), come first as one group per 16-row sub-tile whose slot j IS output
+ *         row 16 s + j (input row -1 where the neighbour is missing); byte 3 of word 2 carries flags telling
+ *         the large-input kernel to keep that sub-tile's sums in registers across those groups (1: C = 0,
+ *         2: do not store D, 4: C = previous D).  The other offsets follow as in layout 0.  Only the
+ *         large-input kernel of b200scn_conv_gpl reads these lists: ask b200scn_conv_gpl_layout. */
 int b200scn_gpl_tile_rows(int64_t n); /* recommended tile_rows for a level of n rows */
 int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows);
 int64_t b200scn_gpl_scratch_bytes(int64_t n_cap);
 int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent, const uint8_t* kofs, int K,
-                      int64_t n_cap, const int32_t* n_dev, int tile_rows, int32_t* tile_off, int32_t* tile_end,
-                      int32_t* total_dev, void* g_rec, int64_t cap_groups, int32_t* koff, void* scratch,
-                      int64_t scratch_bytes, void* stream);
+                      int64_t n_cap, const int32_t* n_dev, int tile_rows, int layout, int32_t* tile_off,
+                      int32_t* tile_end, int32_t* total_dev, void* g_rec, int64_t cap_groups, int32_t* koff,
+                      void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (ii) gather-GEMM(-scatter) convolutions -- SubmanifoldConvolution / Convolution /
@@ -134,14 +141,21 @@ int b200scn_conv_table(const float* in, int64_t ldi, const float* W, int64_t w_s
 
 /* the same contraction driven by a grouped pair list (tensor-core math modes, channels % 16 == 0);
  * tile_end == NULL: scanned lists (stage 0 + 1), else fixed-stride lists (stage 2);
- * n_out_expect: expected live row count when n_out_cap is a capacity (launch heuristics only; 0 = unknown) */
+ * n_out_expect: expected live row count when n_out_cap is a capacity (launch heuristics only; 0 = unknown);
+ * layout: the layout the list was built with */
 /* Wp: optional fragment-ordered copy of W for this direction (b200scn_pack_weights with the same strides
  * and kflip), or NULL.  res (optional, row stride ldr): added to the result -- the shortcut of a residual block. */
 int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
-                     int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
-                     const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int64_t n_out_expect, int Cin,
+                     int64_t w_so, int kflip, int tile_rows, int layout, const int32_t* tile_off,
+                     const int32_t* tile_end, const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev, int64_t n_out_expect, int Cin,
                      int Cout, float* out, int64_t ldo, int accumulate, const float* res, int64_t ldr, int math_mode,
                      void* stream);
+
+/* layout (b200scn_gpl_build) the convolution of these shapes wants its pair list in: 0, or a dense-first
+ * code when the large-input kernel will run (scanned != 0: lists with scanned tile offsets, i.e. tile_end == NULL;
+ * submanifold != 0: the list comes from a submanifold neighbour table). */
+int b200scn_conv_gpl_layout(int tile_rows, int scanned, int64_t n_out_cap, int Cin, int Cout, int K, int submanifold,
+                            int math_mode);
 
 /* Re-order weights into the mma fragment order b200scn_conv_gpl reads with coalesced 16-byte loads.
  * jobs_dev: device array of n_jobs records of int64[10] = {W ptr, out ptr, K, Cin, Cout, w_sk, w_si, w_so, kflip, 0}

@@ -171,14 +171,19 @@ def test_gpl_and_pairs_kernels_agree(mode):
     assert (a - b).abs().max().item() <= (1e-5 if mode == 1 else 2e-3) * a.abs().max().item()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("cin,cout", [(16, 16), (64, 32)])
-def test_large_input_gpl_kernel(mode, cin, cout):
+@pytest.mark.parametrize("mode,cin,cout,layout", [(1, 16, 16, 0), (1, 16, 16, 1), (1, 16, 16, 3), (2, 16, 16, 3),
+                                                  (1, 64, 32, 3), (1, 32, 32, 3), (2, 32, 64, 1)])
+def test_large_input_gpl_kernel(mode, cin, cout, layout):
     """k_conv_gpl (one warp per 128-row tile, weights resident in shared memory -- the kernel bench.py's
-    roofline times) against the neighbour-table kernel.  Runs in a subprocess because the row threshold
-    that selects it is read once per process (B200SCN_GPL_LARGE_MIN_ROWS)."""
+    roofline times) against the neighbour-table kernel, for the three pair-list layouts (offset-major, centre
+    first, centre + last-axis neighbours first); then the module path (SubmanifoldConvolution forward, dgrad and
+    wgrad with the list variant functional._conv_gpl picks) against the FFMA mode.  Runs in a subprocess because
+    the row threshold that selects the kernel is read once per process (B200SCN_GPL_LARGE_MIN_ROWS)."""
     import subprocess
     import sys
+    from uresnet_pytorch_b200.sparseconvnet import config
+    if config.use_tc or config.gpl_min_rows != 0:
+        pytest.skip("subprocess test: one run (under the 'gpl' path id) is enough")
     code = r"""
 import torch, sys
 sys.path.insert(0, %r)
@@ -190,16 +195,17 @@ data, _ = event_blob(6, 96, seed=21)
 coords = torch.from_numpy(data[:, :4]).cuda()
 md = Metadata(3); size = (96, 96, 96)
 lv = md.set_input(coords, size)
-nbr = md.subm_table(size, 3); gpl = md.subm_gpl(size, 3)
+nbr = md.subm_table(size, 3); gpl = md.subm_gpl(size, 3, %d)
 assert gpl["tile_rows"] == 128 and gpl["tile_end"] is None
 n, K, Cin, Cout, mode = lv.n, 27, %d, %d, %d
+assert _lib.load().b200scn_conv_gpl_layout(128, 1, n, Cin, Cout, K, 1, mode) == 1
 torch.manual_seed(1)
 x = torch.randn(n, Cin, device="cuda"); W = torch.randn(K, Cin, Cout, device="cuda") * 0.1
 st = torch.cuda.current_stream().cuda_stream
 for (si, so, flip, ci, co) in ((Cout, 1, 0, Cin, Cout), (1, Cout, 1, Cout, Cin)):
     xin = x if ci == Cin else torch.randn(n, ci, device="cuda")
     a = torch.empty(n, co, device="cuda"); b = torch.empty(n, co, device="cuda")
-    _lib.call("b200scn_conv_gpl", xin.data_ptr(), ci, W.data_ptr(), None, Cin * Cout, si, so, flip, 128,
+    _lib.call("b200scn_conv_gpl", xin.data_ptr(), ci, W.data_ptr(), None, Cin * Cout, si, so, flip, 128, gpl["layout"],
               gpl["tile_off"].data_ptr(), None, gpl["g_rec"].data_ptr(), K, n, None, 0, ci, co, a.data_ptr(), co, 0, None, 0,
               mode, st)
     _lib.call("b200scn_conv_table", xin.data_ptr(), ci, W.data_ptr(), Cin * Cout, si, so, flip, nbr.data_ptr(),
@@ -208,8 +214,26 @@ for (si, so, flip, ci, co) in ((Cout, 1, 0, Cin, Cout), (1, Cout, 1, Cout, Cin))
     tol = 3e-5 if mode == 1 else 5e-3
     err = (a - b).abs().max().item() / b.abs().max().item()
     assert err <= tol, err
+# module path: forward, dgrad, wgrad with the variant list the library asks for
+scn.config.use_tc = False
+coords_l = torch.from_numpy(data[:, :4]).long().cuda()
+feats = torch.randn(len(data), Cin, device="cuda")
+conv = scn.SubmanifoldConvolution(3, Cin, Cout, 3, False).cuda()
+res = {}
+for m in (0, mode):
+    f = feats.clone().requires_grad_(True)
+    conv.weight.grad = None
+    with scn.math(m):
+        xs = scn.InputLayer(3, torch.LongTensor(size), 3)((coords_l, f))
+        y = conv(xs)
+        assert m == 0 or any(len(k) == 3 for k in y.metadata.levels[size].gpl), y.metadata.levels[size].gpl.keys()
+        (y.features * torch.linspace(-1, 1, Cout, device="cuda")).sum().backward()
+    res[m] = (y.features.detach(), f.grad.detach(), conv.weight.grad.detach().clone())
+for a, b in zip(res[0], res[mode]):
+    err = (a - b).abs().max().item() / a.abs().max().item()
+    assert err <= (1e-4 if mode == 1 else 2e-2), err
 print("ok", n)
-""" % (os.path.dirname(os.path.abspath(__file__)), cin, cout, mode)
+""" % (os.path.dirname(os.path.abspath(__file__)), layout, cin, cout, mode)
     env = dict(os.environ, B200SCN_GPL_LARGE_MIN_ROWS="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -26,12 +26,14 @@ SIGNATURES = {
     "b200scn_gpl_tile_rows": (_I32, [_I64]),
     "b200scn_gpl_max_groups": (_I64, [_I64, _I32, _I32]),
     "b200scn_gpl_scratch_bytes": (_I64, [_I64]),
-    "b200scn_gpl_build": (_I32, [_I32, _P, _I64, _P, _P, _I32, _I64, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
+    "b200scn_gpl_build": (_I32, [_I32, _P, _I64, _P, _P, _I32, _I64, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64,
+                                 _P]),
+    "b200scn_conv_gpl_layout": (_I32, [_I32, _I32, _I64, _I32, _I32, _I32, _I32, _I32]),
     "b200scn_wgrad_gpl_scratch_bytes": (_I64, [_I32, _I32, _I32]),
     "b200scn_wgrad_gpl": (_I32, [_P, _I64, _P, _I64, _I32, _P, _P, _I32, _I32, _I64, _P, _I64, _I32, _I32, _P, _I32,
                                  _I32, _P, _I64, _P]),
-    "b200scn_conv_gpl": (_I32, [_P, _I64, _P, _P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _I32, _I64, _P, _I64, _I32,
-                                _I32, _P, _I64, _I32, _P, _I64, _I32, _P]),
+    "b200scn_conv_gpl": (_I32, [_P, _I64, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _I32, _I64, _P, _I64,
+                                _I32, _I32, _P, _I64, _I32, _P, _I64, _I32, _P]),
     "b200scn_pack_weights": (_I32, [_P, _I32, _I64, _P]),
     "b200scn_conv_tc_packed_elems": (_I64, [_I32, _I32, _I32]),
     "b200scn_conv_tc_supported": (_I32, [_I32, _I32, _I32]),

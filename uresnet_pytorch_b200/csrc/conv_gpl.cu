@@ -40,6 +40,7 @@ namespace {
 constexpr int kMaxSmem = 220 * 1024;
 constexpr int kLargeWarps = 20;
 constexpr int kRecRing = 8;  // per-warp shared-memory ring of group records (128 B each)
+constexpr int kPfMax = 3;   // records this many groups ahead are guaranteed to have landed (L2 prefetch distance limit)
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // D(16 pairs x 8 co) += A(16 pairs x 8 ci) * B(8 ci x 8 co)
@@ -50,6 +51,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Record flags (byte 3 of word 2), set by the builder's dense-first layouts and read by k_conv_gpl
+constexpr int kGplCZero = 1;    // C = 0 (first group of a sub-tile: nothing to read)
+constexpr int kGplNoStore = 2;  // D stays in registers (the next group continues the same sub-tile)
+constexpr int kGplCKeep = 4;    // C = the previous group's D (still in registers)
+
 // ---- builder -------------------------------------------------------------------------------------
 // one warp per tile; FILL == false: count groups per tile; FILL == true: write the records
 template <bool FILL, int R>
@@ -57,8 +63,15 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
                             const uint8_t* __restrict__ kofs, int K, int64_t n_cap, const int32_t* __restrict__ n_dev,
                             int32_t* __restrict__ tile_cnt, const int32_t* __restrict__ tile_off,
                             int32_t* __restrict__ tile_beg_out, int4* __restrict__ g_rec, int64_t cap_groups,
-                            int32_t* __restrict__ koff) {
+                            int32_t* __restrict__ koff, int layout) {
   constexpr int NR = R / 32;  // rows per lane
+  // dense-first layouts (submanifold tables only): the centre offset (layout 1), or the centre and the two
+  // neighbours along the last axis (layout 3), are listed FIRST and per 16-row sub-tile -- slot j of such a
+  // group is output row 16 s + j whether or not the neighbour exists (input row -1 = none) -- so that the
+  // convolution kernel keeps the sub-tile's sums in registers across them (flags, see k_conv_gpl)
+  const int kc = (K - 1) >> 1;
+  const int nd = (table != nullptr && parent == nullptr) ? (layout == 3 ? 3 : (layout == 1 ? 1 : 0)) : 0;
+  const int kd0 = kc - (nd >> 1);  // first dense offset
   const int n = live_rows(n_dev, n_cap);
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
@@ -88,6 +101,34 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
       const int r = base + 32 * i + lane;
       nxt[i] = (table != nullptr && parent == nullptr && r < n) ? __ldg(table + r) : -1;
     }
+    if (nd > 0) {
+      const int steps = (R / 16) * nd;
+      if (FILL && grp + steps <= cap_groups) {
+        int32_t* rec = reinterpret_cast<int32_t*>(g_rec + grp * 8);
+        for (int dk = 0; dk < nd; ++dk) {
+          const int k = kd0 + dk;
+          const int flags = (dk == 0 ? kGplCZero : kGplCKeep) | (dk + 1 < nd ? kGplNoStore : 0);
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            const int r = base + 32 * i + lane;
+            // (layout 1: the centre "neighbour" always exists; rows past the end read row 0 into sums nobody stores)
+            const int in_row = r < n ? __ldg(table + (int64_t)k * ld + r) : (nd == 1 ? 0 : -1);
+            const int st = 2 * i + (lane >> 4), j = lane & 15;  // sub-tile, slot
+            int32_t* ent = rec + ((st * nd + dk) * 8 + (j & 7)) * 4;
+            ent[j >> 3] = in_row;
+            reinterpret_cast<unsigned char*>(ent + 2)[j >> 3] = (unsigned char)(16 * st + j);
+            if (j < 8) {
+              unsigned char* b = reinterpret_cast<unsigned char*>(ent + 2);
+              b[2] = (unsigned char)k;
+              b[3] = (unsigned char)flags;
+              ent[3] = 0;
+            }
+          }
+        }
+      }
+      grp += steps;
+      count += steps;
+    }
     for (int k = 0; k < K; ++k) {
       int e[NR], pre[NR];
       int cnt = 0;
@@ -99,7 +140,7 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
         if (parent != nullptr) {
           e[i] = pk[i] == k ? pp[i] : -1;
         } else if (table != nullptr) {
-          e[i] = nxt[i];
+          e[i] = (k >= kd0 && k < kd0 + nd) ? -1 : nxt[i];
           nxt[i] = (k + 1 < K && r < n) ? __ldg(table + (int64_t)(k + 1) * ld + r) : -1;
         } else {
           if (r < n) e[i] = r;
@@ -154,6 +195,8 @@ struct GplParams {
   const float* res; int ldr;  // optional residual added to the result (shortcut of a residual block)
   int warps, split;  // split != 0: the CTA's warps share one tile
   uint32_t ones;     // 0xffffffff (opaque to the compiler)
+  uint32_t zero;     // 0 (opaque to the compiler)
+  int pf;            // k_conv_gpl: L2 prefetch distance in groups (0 = off)
 };
 
 __device__ __forceinline__ float2 lds64(uint32_t a) {
@@ -177,49 +220,67 @@ __device__ __forceinline__ int ldg_nc32(const void* ptr) {
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
-// Q = Cin / 16, MT = output channels of this pass / 16, WSMEM: all K weight slices resident in shared
-// memory in fragment order, X3: 3-term tf32 split, R: tile rows.
+// Dense-first groups (record flags, byte 3 of word 2): the group's 16 slots are the 16 consecutive output rows
+// of one sub-tile, so its running sums stay in the MMA accumulator registers from one group to the next
+// instead of going through the shared-memory accumulator.
+
+// Large inputs.  Q = Cin / 16, MT = output channels of this pass / 16, X3: 3-term tf32 split.  One warp per
+// 128-row tile; all K weight slices resident in shared memory in fragment order.
 //
 // Fragment <-> channel maps (lane = 4 g + t):
 //   A (k-step s = 2q + h): a0/a1 = pair g / g+8 at ci = 16q + 4t + 2h, a2/a3 = same pairs at ci + 1
-//   B (n-tile j):          b0 = W[16q + 4t + 2h][8j + g], b1 = W[16q + 4t + 2h + 1][8j + g]
-//   C/D (n-tile j):        d0,d1 = pair g, co = 8j + 2t, 8j + 2t + 1;  d2,d3 = pair g+8, same co
-// Accumulator row r keeps its 8-channel chunk j at position j ^ x(r), x(r) = (r >> 1) & 1 (MT odd) or
-// r & 3 (MT even), so that the LDS.64/STS.64 of four consecutive rows fall into distinct banks.
-template <int Q, int MT, bool WSMEM, bool X3, int R>
-__global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(const GplParams p) {
-  constexpr int KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
-  constexpr int DEPTH = Q <= 2 ? 3 : 2;  // register slots for gathered feature rows
-  constexpr int LEAD = DEPTH - 1;        // groups between a row request and its use
+//   B (n-tile j = 2mt + jj, column n = g): channel co = 16mt + 4 (g >> 1) + 2 jj + (g & 1);
+//                          b0 = W[16q + 4t + 2h][co], b1 = W[16q + 4t + 2h + 1][co]
+//   C/D (n-tile 2mt + jj):  d0,d1 = pair g, co = 16mt + 4t + 2jj, + 1;  d2,d3 = pair g+8, same co
+// so lane (g, t) owns the four CONSECUTIVE channels 16mt + 4t .. + 3 of its two rows: the scatter-add is one
+// LDS.128 + one STS.128 per (row, mt) on an accumulator kept in natural channel order.  Rows of a 32-channel
+// pass (128 B) swap their 64-byte halves on odd rows, so that the two rows a quarter-warp touches in one
+// shared-memory wavefront collide only when their parities are equal (the same rule as for 64-byte rows).
+//
+// Pipeline (profiles/README.md, round 2): ptxas tracks ALL row gathers of a warp on one scoreboard, and a
+// wait on a scoreboard waits for every load on it -- so the first use of a group's rows also waits for
+// whatever was requested after them.  With rows requested two groups ahead this exposed the full memory
+// latency once per loop trip (20% of all stall samples on one instruction).  Here the rows of group i + 1 are
+// requested right AFTER the first use of the rows of group i (their address carries a data dependence on a
+// loaded value, so ptxas cannot hoist them): every wait then only covers loads that are a whole group old.
+template <int Q, int MT, bool X3, bool D3, bool A128>
+__global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParams p) {
+  // A128: accumulator rows in natural channel order, one LDS.128 / STS.128 per (row, 16 channels) -- half the
+  // shared-memory wavefronts of the alternative, but the loaded quads hold two n-tiles of ONE row while an HMMA
+  // accumulator quad holds one n-tile of TWO rows: 16 register moves per group.  !A128: n-tile j of a row is an
+  // 8-byte piece, LDS.64 / STS.64 straight into / out of the accumulator quads (column map: co = 8j + 2t (+1)).
+  // D3: the list may hold layout-3 groups (missing neighbours as input row -1, sums kept in registers across
+  // groups); otherwise only "C = 0" groups (layout 1) need support
+  constexpr int R = 128, KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
   // WREG: the B fragments of the current offset live in registers and are reloaded (raw fp32 from shared
   // memory, low parts recomputed) only when the offset changes -- the L1/shared data pipe is this
   // kernel's bottleneck (profiles/README.md), and the weights were a third of its shared-memory traffic
-  constexpr bool WREG = WSMEM && (Q * MT <= 2);
-  constexpr bool WLO = false;  // (no separate low-part copy: shared memory holds raw fp32, low parts are recomputed)
+  constexpr bool WREG = (Q * MT <= 2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_wait();
   const int n = live_rows(p.n_dev, p.n_cap);
   const int warps = p.warps;
-  const int split = p.split;
-  if (split ? ((int64_t)blockIdx.x * R >= n) : (n == 0)) return;
+  if (n == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K;
   const int cob = blockIdx.y * CT;
 
-  const int w_elems = WSMEM ? K * KS * MT * 128 : 0;
+  const int w_elems = K * KS * MT * 128;
   float* Whi = reinterpret_cast<float*>(smem_raw);
-  float* Wlo = Whi + w_elems;
   constexpr int kAccBytes = (R + 1) * CT * 4;
-  const int acc_base = w_elems * 4 * (WLO ? 2 : 1);
+  const int acc_base = w_elems * 4;
   float4* const acc = reinterpret_cast<float4*>(smem_raw + acc_base + warp * kAccBytes);
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const uint32_t s_acc = s_base + acc_base + warp * kAccBytes + t * 8;  // + row * CT * 4 + chunk * 32
+  const uint32_t s_acc = s_base + acc_base + warp * kAccBytes;  // + row * CT * 4 + chunk * 16
   const uint32_t s_whi = s_base + lane * 16;
   const uint32_t s_ring = s_base + acc_base + warps * kAccBytes + warp * (kRecRing * 128);
 
-  if (WSMEM) {
+  {
     // fragment order: [(k, kstep s, mt)][lane][4] = {b0, b1 of n-tile 2mt, b0, b1 of n-tile 2mt+1}
     const bool co_fast = (p.w_so == 1);
     const int fast_n = co_fast ? CT : 16 * Q, slow_n = co_fast ? 16 * Q : CT;
@@ -234,25 +295,23 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       const float v = __ldg(p.W + (int64_t)kk * p.w_sk + (int64_t)ci * p.w_si + (int64_t)(cob + col) * p.w_so);
       const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
       const int s = ((ci >> 4) << 1) + (rem >> 1);
-      const int mt = col >> 4, odd = (col >> 3) & 1, gg = col & 7;
-      const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + odd * 2 + (rem & 1);
-      const float hi = tf32_hi(v);
-      (void)hi; (void)Wlo;
+      const int mt = col >> 4;
+      const int jj = A128 ? (col >> 1) & 1 : (col >> 3) & 1;
+      const int gg = A128 ? ((((col & 15) >> 2) << 1) | (col & 1)) : (col & 7);
+      const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + jj * 2 + (rem & 1);
       Whi[dst] = v;  // raw fp32: the tensor core truncates the high part itself, the low part is recomputed
     }
     __syncthreads();
   }
 
   const int64_t n_tiles = ((int64_t)n + R - 1) / R;
-  // Tile -> warp assignment.  Split mode: tile = CTA.  Otherwise every warp takes a CONTIGUOUS range of
-  // tiles of (nearly) equal cost, cost(tile) = groups + kTileCost: the work per tile varies 10x between
-  // track and shower regions, and a round-robin assignment left the SMs idle for 20% of the kernel.
-  // cost is monotone in the tile index (prefix sums), so the range bounds are two binary searches.
+  // Tile -> warp assignment: every warp takes a CONTIGUOUS range of tiles of (nearly) equal cost,
+  // cost(tile) = groups + kTileCost: the work per tile varies 10x between track and shower regions, and a
+  // round-robin assignment left the SMs idle for 20% of the kernel.  cost is monotone in the tile index
+  // (prefix sums), so the range bounds are two binary searches.
   constexpr int kTileCost = 4;
-  int64_t wt_begin, wt_end, wt_stride;
-  if (split) {
-    wt_begin = blockIdx.x; wt_end = n_tiles; wt_stride = gridDim.x;
-  } else {
+  int64_t wt_begin, wt_end;
+  {
     const int64_t nw = (int64_t)gridDim.x * warps, w = (int64_t)blockIdx.x * warps + warp;
     const int64_t total = (int64_t)__ldg(p.tile_off + n_tiles) + kTileCost * n_tiles;
     const int64_t lo_cost = total * w / nw, hi_cost = total * (w + 1) / nw;
@@ -265,32 +324,35 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
       if (a0 < a1) { if (ca >= lo_cost) a1 = ma; else a0 = ma + 1; }
       if (b0 < b1) { if (cb >= hi_cost) b1 = mb; else b0 = mb + 1; }
     }
-    wt_begin = a0; wt_end = (w == nw - 1) ? n_tiles : b0; wt_stride = 1;
+    wt_begin = a0; wt_end = (w == nw - 1) ? n_tiles : b0;
   }
   const char* const in_l = reinterpret_cast<const char*>(p.in) + 16 * t;
   const uint32_t ldb = (uint32_t)p.ldi * 4u;  // row stride in bytes
-  for (int64_t wt = wt_begin; wt < wt_end; wt += wt_stride) {
+  const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  // accumulator address of (row, mt) for this lane: 16-byte chunk 4mt + t, halves swapped on odd rows (MT == 2)
+  auto acc_addr = [&](int row, int mt) -> uint32_t {
+    const int chunk = (4 * mt + t) ^ ((MT == 2) ? ((row & 1) << 2) : 0);
+    return s_acc + (uint32_t)row * (CT * 4) + (uint32_t)chunk * 16u;
+  };
+  // !A128: 8-channel piece j of a row sits at position j ^ x(row), x = (row >> 1) & 1 (MT odd) or row & 3 (MT
+  // even), so that the LDS.64 / STS.64 of four consecutive rows fall into distinct banks
+  auto acc_addr64 = [&](int row, int j) -> uint32_t {
+    const int x = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
+    return s_acc + (uint32_t)row * (CT * 4) + (uint32_t)((j ^ x) << 5) + (uint32_t)t * 8u;
+  };
+  for (int64_t wt = wt_begin; wt < wt_end; ++wt) {
     const int base = (int)(wt * R);
     __syncwarp();
     for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // this warp's group range
-    int gb = __ldg(p.tile_off + wt), ge = __ldg(p.tile_off + wt + 1);
-    if (split) {
-      const int per = (ge - gb + warps - 1) / warps;
-      const int b2 = gb + warp * per;
-      ge = min(ge, b2 + per);
-      gb = min(b2, ge);
-    }
+    const int gb = __ldg(p.tile_off + wt), ge = __ldg(p.tile_off + wt + 1);
     __syncwarp();
 
-    // Software pipeline.  Group records stream through a per-warp shared-memory ring filled by cp.async
-    // kRecRing - 1 groups ahead (an async copy has no destination register, so ptxas cannot sink it next
-    // to its use the way it does with plain loads -- profiles/README.md); the feature rows of group
-    // i + LEAD are requested at the START of group i's body into one of DEPTH register slots.  The body is
-    // unrolled DEPTH times so every slot index is static.  Records and rows past the end of the range
-    // are clamped to the last group: redundant but unconditional, never consumed.
-    float4 G[DEPTH][2][Q];
-    int Rz[DEPTH];
+    // Group records stream through a per-warp shared-memory ring filled by cp.async kRecRing - 1 groups ahead
+    // (an async copy has no destination register, so ptxas cannot sink it next to its use the way it does
+    // with plain loads).  Records and rows past the end of the range are clamped to the last group:
+    // redundant but unconditional, never consumed.
+    float4 G[2][2][Q];
+    int Rz[2];
     const int g_last = max(ge - 1, gb);
     const uint32_t ring_cp = s_ring + lane * 4, ring_rd = s_ring + g * 16;
     auto fetch_rec = [&](int grp) {  // lane l copies word l of the 128-byte record
@@ -299,56 +361,89 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
                    "l"(src) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto fetch_rows = [&](int grp, int d) {  // record of `grp` must have landed in the ring
+    // rows of group `grp` (its record must have landed in the ring) into register slot d; `dep` is zero, but
+    // only at run time: it ties the request to the value it was derived from.  A negative input row (a missing
+    // neighbour in a dense-first group) contributes zeros.
+    auto fetch_rows = [&](int grp, int d, uint32_t dep) {
       const float4 r = lds128(ring_rd + (uint32_t)(grp & (kRecRing - 1)) * 128u);
       Rz[d] = __float_as_int(r.z);
-      const float4* s0 = reinterpret_cast<const float4*>(in_l + (uint64_t)__float_as_uint(r.x) * ldb);
-      const float4* s1 = reinterpret_cast<const float4*>(in_l + (uint64_t)__float_as_uint(r.y) * ldb);
+      const int i0 = __float_as_int(r.x), i1 = __float_as_int(r.y);
+      if (D3) {
+        const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)max(i0, 0) * ldb);
+        const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)max(i1, 0) * ldb);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        G[d][0][q] = __ldg(s0 + 4 * q);
-        G[d][1][q] = __ldg(s1 + 4 * q);
+        for (int q = 0; q < Q; ++q) {
+          G[d][0][q] = i0 >= 0 ? __ldg(s0 + 4 * q) : z4;
+          G[d][1][q] = i1 >= 0 ? __ldg(s1 + 4 * q) : z4;
+        }
+      } else {
+        const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i0 * ldb);
+        const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i1 * ldb);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          G[d][0][q] = __ldg(s0 + 4 * q);
+          G[d][1][q] = __ldg(s1 + 4 * q);
+        }
       }
     };
     if (gb < ge) {
       __syncwarp();  // the previous tile's last ring reads are done
 #pragma unroll
       for (int u = 0; u < kRecRing - 1; ++u) fetch_rec(gb + u);
-      asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - LEAD) : "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - kPfMax) : "memory");
       __syncwarp();
-#pragma unroll
-      for (int d = 0; d < LEAD; ++d) fetch_rows(gb + d, d);
+      fetch_rows(gb, 0, 0u);
     }
 
     uint32_t wbh[WREG ? KS : 1][WREG ? MT : 1][4], wbl[WREG ? KS : 1][WREG ? MT : 1][4];
     int wcur = -1;
-    for (int g0 = gb; g0 < ge; g0 += DEPTH) {
+    float dacc[NT][4];
 #pragma unroll
-      for (int u = 0; u < DEPTH; ++u) {
+    for (int j = 0; j < NT; ++j) dacc[j][0] = dacc[j][1] = dacc[j][2] = dacc[j][3] = 0.f;
+    for (int g0 = gb; g0 < ge; g0 += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
         const int grp = g0 + u;
         if (grp >= ge) break;
         const int d = u;
-        // (g0 - gb) is a multiple of DEPTH, so group `grp` sits in row slot u and group grp + LEAD in
-        // slot (u + LEAD) % DEPTH -- the slot released by group grp - 1
         fetch_rec(grp + kRecRing - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - LEAD) : "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - kPfMax) : "memory");  // records up to grp + kPfMax have landed
         __syncwarp();
-        fetch_rows(grp + LEAD, (u + LEAD) % DEPTH);
-        const uint32_t mz = (uint32_t)Rz[d];
-        const int kk = (mz >> 16) & 0xff;
-        const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
-        const int x0 = (MT & 1) ? ((o0 >> 1) & 1) : (o0 & 3), x1 = (MT & 1) ? ((o1 >> 1) & 1) : (o1 & 3);
-        const uint32_t a0 = s_acc + o0 * (CT * 4), a1 = s_acc + o1 * (CT * 4);
-        // C operand: the running sums of the 16 output rows
-        float dacc[NT][4];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const float2 c01 = lds64(a0 + ((j ^ x0) << 5)), c23 = lds64(a1 + ((j ^ x1) << 5));
-          dacc[j][0] = c01.x; dacc[j][1] = c01.y; dacc[j][2] = c23.x; dacc[j][3] = c23.y;
+        // first use of this group's rows, then the request for the next group's
+        const uint32_t dep = __float_as_uint(G[d][0][0].x) & p.zero;
+        fetch_rows(grp + 1, d ^ 1, dep);
+        if (p.pf) {
+          // rows of a group further ahead: L2 prefetch (no destination register, hence no scoreboard) -- turns
+          // the DRAM misses among them (60% of the gathers miss L2) into L2 hits by the time they are requested
+          const float4 r = lds128(ring_rd + (uint32_t)((grp + p.pf) & (kRecRing - 1)) * 128u);
+          const int i0 = __float_as_int(r.x), i1 = __float_as_int(r.y);
+          if (!D3 || i0 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_l + (uint64_t)(uint32_t)i0 * ldb));
+          if (!D3 || i1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_l + (uint64_t)(uint32_t)i1 * ldb));
         }
-        const int kwt = p.kflip ? (K - 1 - kk) : kk;
-        const float* wk = WSMEM ? nullptr : p.W + (int64_t)kwt * p.w_sk + (int64_t)(4 * t) * p.w_si +
-                                                (int64_t)(cob + g) * p.w_so;
+        const uint32_t mz = (uint32_t)Rz[d];
+        const int kk = (mz >> 16) & 0xff, fl = (int)(mz >> 24);
+        const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
+        // C operand: the running sums of the 16 output rows
+        if (fl & kGplCZero) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dacc[j][0] = dacc[j][1] = dacc[j][2] = dacc[j][3] = 0.f;
+        } else if (!D3 || !(fl & kGplCKeep)) {
+          if (A128) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const float4 c0 = lds128(acc_addr(o0, mt)), c1 = lds128(acc_addr(o1, mt));
+              dacc[2 * mt][0] = c0.x; dacc[2 * mt][1] = c0.y; dacc[2 * mt + 1][0] = c0.z; dacc[2 * mt + 1][1] = c0.w;
+              dacc[2 * mt][2] = c1.x; dacc[2 * mt][3] = c1.y; dacc[2 * mt + 1][2] = c1.z; dacc[2 * mt + 1][3] = c1.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              const float2 c01 = lds64(acc_addr64(o0, j)), c23 = lds64(acc_addr64(o1, j));
+              dacc[j][0] = c01.x; dacc[j][1] = c01.y; dacc[j][2] = c23.x; dacc[j][3] = c23.y;
+            }
+          }
+        }
         const uint32_t wk_off = (uint32_t)kk * (KS * MT * 512);
         if (WREG && kk != wcur) {
           wcur = kk;
@@ -396,23 +491,13 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
                   bh[r >> 1][r & 1] = wbh[WREG ? s : 0][WREG ? mt : 0][r];
                   bl[r >> 1][r & 1] = wbl[WREG ? s : 0][WREG ? mt : 0][r];
                 }
-              } else if (WSMEM) {
+              } else {
                 const float4 b4 = lds128(s_whi + wk_off + (s * MT + mt) * 512);
                 const float w4[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                   bh[r >> 1][r & 1] = __float_as_uint(w4[r]);
                   if (X3) bl[r >> 1][r & 1] = __float_as_uint(w4[r] - tf32_hi(w4[r]));
-                }
-              } else {
-                const float* wp = wk + (int64_t)(16 * q + 2 * h) * p.w_si + (int64_t)(16 * mt) * p.w_so;
-                const float w4[4] = {__ldg(wp), __ldg(wp + p.w_si), __ldg(wp + 8 * p.w_so),
-                                     __ldg(wp + p.w_si + 8 * p.w_so)};
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                  const float hi = X3 ? tf32_hi(w4[r]) : w4[r];
-                  bh[r >> 1][r & 1] = __float_as_uint(hi);
-                  bl[r >> 1][r & 1] = __float_as_uint(w4[r] - hi);
                 }
               }
 #pragma unroll
@@ -426,35 +511,37 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
             }
           }
         }
+        if (!D3 || !(fl & kGplNoStore)) {
+          if (A128) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          sts64(a0 + ((j ^ x0) << 5), dacc[j][0], dacc[j][1]);
-          sts64(a1 + ((j ^ x1) << 5), dacc[j][2], dacc[j][3]);
+            for (int mt = 0; mt < MT; ++mt) {
+              sts128(acc_addr(o0, mt), dacc[2 * mt][0], dacc[2 * mt][1], dacc[2 * mt + 1][0], dacc[2 * mt + 1][1]);
+              sts128(acc_addr(o1, mt), dacc[2 * mt][2], dacc[2 * mt][3], dacc[2 * mt + 1][2], dacc[2 * mt + 1][3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              sts64(acc_addr64(o0, j), dacc[j][0], dacc[j][1]);
+              sts64(acc_addr64(o1, j), dacc[j][2], dacc[j][3]);
+            }
+          }
         }
         __syncwarp();
       }
     }
 
     __syncwarp();
-    if (split) __syncthreads();
-    const bool vec_ok = (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    const int e_begin = split ? tid : lane, e_step = split ? (int)blockDim.x : 32;
-    const float4* acc0 = reinterpret_cast<const float4*>(smem_raw + acc_base);
-    for (int e = e_begin; e < R * C4; e += e_step) {
+    for (int e = lane; e < R * C4; e += 32) {
       const int row = e / C4, c4 = e - row * C4;
       if (base + row < n) {
-        const int xr = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
-        const int src = row * C4 + ((((c4 >> 1) ^ xr) << 1) | (c4 & 1));
-        float4 v;
-        if (split) {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int w = 0; w < warps; ++w) {
-            const float4 u = acc0[w * (kAccBytes / 16) + src];
-            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-          }
+        int src;
+        if (A128) {
+          src = row * C4 + (c4 ^ ((MT == 2) ? ((row & 1) << 2) : 0));
         } else {
-          v = acc[src];
+          const int xr = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
+          src = row * C4 + ((((c4 >> 1) ^ xr) << 1) | (c4 & 1));
         }
+        float4 v = acc[src];
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
         if (p.res != nullptr) {
           const float* rr = p.res + (int64_t)(base + row) * p.ldr + cob + 4 * c4;
@@ -472,7 +559,6 @@ __global__ void __launch_bounds__(WSMEM ? kLargeWarps * 32 : 256, 1) k_conv_gpl(
         }
       }
     }
-    if (split) __syncthreads();
   }
 }
 
@@ -683,11 +769,11 @@ int large_warps() {
 }
 
 // ---- large inputs: k_conv_gpl, one warp per tile, weights resident in shared memory ---------------
-template <int Q, int MT, bool X3>
+template <int Q, int MT, bool X3, bool D3, bool A128>
 int launch_large(GplParams p, int passes, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, true, X3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, X3, D3, A128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kMaxSmem));
     configured = true;
   }
@@ -697,22 +783,42 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   while (warps > 1 && fixed + warps * per_warp > (size_t)kMaxSmem) --warps;
   p.warps = warps;
   p.split = 0;
+  static int pf = -1;  // B200SCN_GPL_PF: L2 prefetch distance in groups, 0 = off, at most kPfMax (A/B runs)
+  if (pf < 0) {
+    const char* e = getenv("B200SCN_GPL_PF");
+    pf = e ? atoi(e) : 0;
+    if (pf < 0 || pf > kPfMax) pf = 0;
+  }
+  p.pf = pf;
   const int64_t tiles = cdiv(p.n_cap, 128);
   int64_t gx = cdiv(tiles, warps);
   int64_t gmax = sm_count() / passes;
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  launch_pdl(k_conv_gpl<Q, MT, true, X3, 128>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
+  launch_pdl(k_conv_gpl<Q, MT, X3, D3, A128>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
 }
 
 template <int Q>
-int launch_large_q(const GplParams& p, int MT, int passes, int x3, cudaStream_t st) {
-  if (MT == 1) return x3 ? launch_large<Q, 1, true>(p, passes, st) : launch_large<Q, 1, false>(p, passes, st);
-  return x3 ? launch_large<Q, 2, true>(p, passes, st) : launch_large<Q, 2, false>(p, passes, st);
+int launch_large_q(const GplParams& p, int MT, int passes, int x3, int d3, cudaStream_t st) {
+  static int a128 = -1;  // B200SCN_GPL_ACC128 = 0 / 1: accumulator access width (A/B runs)
+  if (a128 < 0) {
+    const char* e = getenv("B200SCN_GPL_ACC128");
+    a128 = e ? (atoi(e) != 0) : 1;
+  }
+  if (d3) {  // layout-3 lists (A/B runs): tf32x3 only
+    if (MT == 1) return launch_large<Q, 1, true, true, true>(p, passes, st);
+    return launch_large<Q, 2, true, true, true>(p, passes, st);
+  }
+  if (!a128 && x3) {
+    if (MT == 1) return launch_large<Q, 1, true, false, false>(p, passes, st);
+    return launch_large<Q, 2, true, false, false>(p, passes, st);
+  }
+  if (MT == 1) return x3 ? launch_large<Q, 1, true, false, true>(p, passes, st) : launch_large<Q, 1, false, false, true>(p, passes, st);
+  return x3 ? launch_large<Q, 2, true, false, true>(p, passes, st) : launch_large<Q, 2, false, false, true>(p, passes, st);
 }
 
 // ---- small inputs: k_conv_gpl_small ---------------------------------------------------------------
@@ -828,19 +934,19 @@ template <bool FILL>
 static void launch_build(int tile_rows, int grid, int threads, cudaStream_t st, const int32_t* table, int64_t ld,
                          const int32_t* parent, const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev,
                          int32_t* tile_cnt, const int32_t* tile_off, int32_t* tile_beg_out, int4* rec, int64_t cap,
-                         int32_t* koff) {
+                         int32_t* koff, int layout) {
   switch (tile_rows) {
     case 32:
       k_gpl_build<FILL, 32><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                      tile_beg_out, rec, cap, koff);
+                                                      tile_beg_out, rec, cap, koff, layout);
       break;
     case 64:
       k_gpl_build<FILL, 64><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                      tile_beg_out, rec, cap, koff);
+                                                      tile_beg_out, rec, cap, koff, layout);
       break;
     default:
       k_gpl_build<FILL, 128><<<grid, threads, 0, st>>>(table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt, tile_off,
-                                                       tile_beg_out, rec, cap, koff);
+                                                       tile_beg_out, rec, cap, koff, layout);
   }
 }
 
@@ -850,12 +956,15 @@ static void launch_build(int tile_rows, int grid, int threads, cudaStream_t st, 
  *          (begin) and tile_end[tiles]; no scan, nothing to read back -- the static (CUDA graph) regime. */
 extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, const int32_t* parent,
                                  const uint8_t* kofs, int K, int64_t n_cap, const int32_t* n_dev, int tile_rows,
-                                 int32_t* tile_off, int32_t* tile_end, int32_t* total_dev, void* g_rec,
+                                 int layout, int32_t* tile_off, int32_t* tile_end, int32_t* total_dev, void* g_rec,
                                  int64_t cap_groups, int32_t* koff, void* scratch, int64_t scratch_bytes,
                                  void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= 64, "gpl_build: K must be 1..64");
   B200_CHECK_ARG(tile_rows == 32 || tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 32, 64 or 128");
+  B200_CHECK_ARG(layout == 0 || ((layout == 1 || layout == 3) && table != nullptr && parent == nullptr && (K & 1) &&
+                                 K >= 3 && koff == nullptr),
+                 "gpl_build: dense-first layouts (1, 3) need a submanifold table with an odd offset count and no koff");
   B200_CHECK_ARG(stage == 2 || scratch_bytes >= b200scn_gpl_scratch_bytes(n_cap), "gpl_build: scratch too small");
   const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(scratch);
@@ -870,25 +979,61 @@ extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, co
     B200_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(tiles + 8) * 4, st));
     if (n_cap > 0)
       launch_build<false>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_cnt,
-                          nullptr, nullptr, nullptr, 0, nullptr);
+                          nullptr, nullptr, nullptr, 0, nullptr, layout);
     // exclusive scan over all `tiles` counts (tiles beyond the live ones hold 0)
     if (int rc = scan_i32_public(tile_cnt, tile_off, tiles, nullptr, total_dev, tile_off, bsums, st)) return rc;
     count_launches(4);
   } else if (stage == 1) {
     if (n_cap > 0)
       launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, nullptr,
-                         tile_off, nullptr, rec, cap_groups, koff);
+                         tile_off, nullptr, rec, cap_groups, koff, layout);
     count_launches(1);
   } else {
     B200_CHECK_ARG(tile_end != nullptr, "gpl_build: stage 2 needs tile_end");
     B200_CHECK_ARG(cap_groups >= b200scn_gpl_max_groups(n_cap, K, tile_rows), "gpl_build: stage 2 needs worst-case capacity");
     if (n_cap > 0)
       launch_build<true>(tile_rows, (int)grid, warps * 32, st, table, ld, parent, kofs, K, n_cap, n_dev, tile_end,
-                         nullptr, tile_off, rec, cap_groups, koff);
+                         nullptr, tile_off, rec, cap_groups, koff, layout);
     count_launches(1);
   }
   B200_CHECK_LAUNCH("gpl_build");
   return 0;
+}
+
+// Large inputs (enough 128-row tiles to give every SM a CTA of one-tile warps) with scanned lists and a weight
+// slice that fits in shared memory next to >= 12 accumulators take k_conv_gpl; returns its pass width MT
+// (output channels / 16 per pass) or 0 for the small-input kernel.  (Wider inputs take the small-input kernel,
+// which walks any Cin in one launch: measured equal on the 768^3 / uf=32 configuration, with a third fewer
+// launches.)
+static int large_pass_width(int tile_rows, bool scanned, int64_t n_out_cap, int Cin, int Cout, int K, int x3) {
+  static int64_t large_min = -1;  // B200SCN_GPL_LARGE_MIN_ROWS overrides the row threshold (tests)
+  if (large_min < 0) {
+    const char* e = getenv("B200SCN_GPL_LARGE_MIN_ROWS");
+    large_min = e ? atoll(e) : (int64_t)128 * 8 * sm_count();
+  }
+  if (!(tile_rows == 128 && scanned && Cin <= 64 && n_out_cap >= large_min)) return 0;
+  const int cot = Cout / 16;
+  for (int mt = 2; mt >= 1; --mt)
+    if (cot % mt == 0 && w_smem_bytes(K, Cin, mt, x3) + 12 * (acc_bytes(128, mt) + kRecRing * 128) <= (size_t)kMaxSmem)
+      return mt;
+  return 0;
+}
+
+/* Pair-list layout the convolution of these shapes wants (b200scn_gpl_build's `layout`): 0 = offset-major groups
+ * only (every kernel reads it), 1 / 3 = dense-first (the large-input kernel only).  B200SCN_GPL_DENSE overrides
+ * the dense-first choice (0 / 1 / 3, A/B runs). */
+extern "C" int b200scn_conv_gpl_layout(int tile_rows, int scanned, int64_t n_out_cap, int Cin, int Cout, int K,
+                                       int submanifold, int math_mode) {
+  static int dense = -1;
+  if (dense < 0) {
+    const char* e = getenv("B200SCN_GPL_DENSE");
+    dense = e ? atoi(e) : 1;
+    if (dense != 0 && dense != 1 && dense != 3) dense = 1;
+  }
+  if (!submanifold || !(K & 1) || K < 3 || Cin % 16 || Cout % 16) return 0;
+  const int x3 = math_mode == B200SCN_MATH_TF32X3 ? 1 : 0;
+  if (!large_pass_width(tile_rows, scanned != 0, n_out_cap, Cin, Cout, K, x3)) return 0;
+  return (dense == 3 && !x3) ? 1 : dense;
 }
 
 extern "C" int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, void* stream) {
@@ -904,8 +1049,8 @@ extern "C" int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t
 }
 
 extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* Wp, int64_t w_sk, int64_t w_si,
-                                int64_t w_so, int kflip, int tile_rows, const int32_t* tile_off, const int32_t* tile_end,
-                                const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev,
+                                int64_t w_so, int kflip, int tile_rows, int layout, const int32_t* tile_off,
+                                const int32_t* tile_end, const void* g_rec, int K, int64_t n_out_cap, const int32_t* n_out_dev,
                                 int64_t n_out_expect, int Cin, int Cout, float* out, int64_t ldo, int accumulate,
                                 const float* res, int64_t ldr, int math_mode, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -924,31 +1069,20 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   p.tile_off = tile_off; p.tile_end = tile_end; p.g_rec = reinterpret_cast<const int4*>(g_rec); p.Q = Cin / 16;
   p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = accumulate;
   p.res = res; p.ldr = (int)ldr;
-  p.warps = 8; p.split = 1; p.ones = 0xffffffffu;
+  p.warps = 8; p.split = 1; p.ones = 0xffffffffu; p.zero = 0u; p.pf = 0;
 
-  // large inputs (enough 128-row tiles to give every SM a CTA of one-tile warps) with scanned lists and
-  // a weight slice that fits in shared memory next to >= 12 accumulators: k_conv_gpl
-  static int64_t large_min = -1;  // B200SCN_GPL_LARGE_MIN_ROWS overrides the row threshold (tests)
-  if (large_min < 0) {
-    const char* e = getenv("B200SCN_GPL_LARGE_MIN_ROWS");
-    large_min = e ? atoll(e) : (int64_t)128 * 8 * sm_count();
-  }
-  // (wider inputs take the small-input kernel below, which walks any Cin in one launch: measured equal on
-  // the 768^3 / uf=32 configuration, with a third fewer launches)
-  const bool large = tile_rows == 128 && tile_end == nullptr && Cin <= 64 && n_out_cap >= large_min;
-  if (large) {
-    int MT = 0;
-    for (int mt = 2; mt >= 1; --mt)
-      if (cot % mt == 0 && w_smem_bytes(K, Cin, mt, x3) + 12 * (acc_bytes(128, mt) + kRecRing * 128) <= (size_t)kMaxSmem) { MT = mt; break; }
-    if (MT) {
-      switch (p.Q) {
-        case 1: return launch_large_q<1>(p, MT, cot / MT, x3, st);
-        case 2: return launch_large_q<2>(p, MT, cot / MT, x3, st);
-        case 3: return launch_large_q<3>(p, MT, cot / MT, x3, st);
-        default: return launch_large_q<4>(p, MT, cot / MT, x3, st);
-      }
+  const int MTL = large_pass_width(tile_rows, tile_end == nullptr, n_out_cap, Cin, Cout, K, x3);
+  B200_CHECK_ARG(layout != 3 || x3, "conv_gpl: layout-3 pair lists are served in the tf32x3 mode only");
+  if (MTL) {
+    switch (p.Q) {
+      case 1: return launch_large_q<1>(p, MTL, cot / MTL, x3, layout == 3, st);
+      case 2: return launch_large_q<2>(p, MTL, cot / MTL, x3, layout == 3, st);
+      case 3: return launch_large_q<3>(p, MTL, cot / MTL, x3, layout == 3, st);
+      default: return launch_large_q<4>(p, MTL, cot / MTL, x3, layout == 3, st);
     }
   }
+  B200_CHECK_ARG(layout == 0, "conv_gpl: a dense-first pair list (layout 1 / 3) only serves the large-input kernel "
+                              "(ask b200scn_conv_gpl_layout first)");
   // small inputs: narrow passes unless the tiles alone already cover the SMs twice
   // (n_out_expect: how many rows the level really has when n_out_cap is only a buffer capacity)
   const int64_t n_live = (n_out_expect > 0 && n_out_expect < n_out_cap) ? n_out_expect : n_out_cap;

@@ -259,9 +259,16 @@ def _conv_gpl(x, W, W3, w_si, w_so, kflip, gpl, n_out, n_out_dev, Cin, Cout, mat
     """out[o] = sum over the pair list's (in -> o, k) rules of x[in] @ W[k] (strided view of W3)."""
     K = W3.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    if gpl.get("variant") is not None:
+        # submanifold list: the large-input kernel wants the dense offsets first (metadata.subm_gpl)
+        want = _lib.load().b200scn_conv_gpl_layout(gpl["tile_rows"], int(gpl["tile_end"] is None), n_out, Cin, Cout, K, 1,
+                                                   math)
+        if want:
+            gpl = gpl["variant"](want)
     Wp = packed_weights(W, W3, Cin, Cout, w_si, w_so, kflip)["buf"].data_ptr() if config.pack_weights else None
     _lib.call("b200scn_conv_gpl", x.data_ptr(), x.stride(0), W3.data_ptr(), Wp, W3.shape[1] * W3.shape[2], w_si, w_so,
-              kflip, gpl["tile_rows"], gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]), gpl["g_rec"].data_ptr(), K,
+              kflip, gpl["tile_rows"], gpl.get("layout", 0), gpl["tile_off"].data_ptr(), _lib.ptr(gpl["tile_end"]),
+              gpl["g_rec"].data_ptr(), K,
               n_out, n_out_dev, gpl.get("rows_hint", 0),
               Cin, Cout, out.data_ptr(), out.stride(0), 0, _lib.ptr(res), res.stride(0) if res is not None else 0, math,
               _stream())

@@ -12,6 +12,8 @@ Two shape regimes:
     count as its capacity and the kernels take the live count from device memory.  This is
     the regime a whole training step is captured in as one CUDA graph.
 """
+import weakref
+
 import torch
 
 from .. import _lib
@@ -221,8 +223,10 @@ class Metadata(object):
         return rules
 
     # -- grouped pair lists (tensor-core convolution input) ------------------------------------
-    def _build_gpl(self, lv, table, parent, kofs, K, size_key=None):
-        """Pair list over the rows of `lv` (the OUTPUT rows of the convolution that will use it)."""
+    def _build_gpl(self, lv, table, parent, kofs, K, size_key=None, layout=0):
+        """Pair list over the rows of `lv` (the OUTPUT rows of the convolution that will use it).
+        layout: b200scn_gpl_build's (0 = offset-major, read by every kernel; 1 / 3 = dense-first, large-input
+        convolution kernel only -- no per-offset index, so no weight gradient walks it)."""
         L = _lib.load()
         rows = lv.rows
         nd = self.n_dev_ptr(lv)
@@ -231,9 +235,10 @@ class Metadata(object):
         tiles = max((max(rows, 1) + tile - 1) // tile, 1)
         dev = self.device
         tile_off = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
-        koff = torch.empty(tiles * (K + 1), dtype=torch.int32, device=dev)  # per-(tile, offset) group index
+        # per-(tile, offset) group index
+        koff = torch.empty(tiles * (K + 1), dtype=torch.int32, device=dev) if layout == 0 else None
         tab = (_lib.ptr(table), table.stride(0) if table is not None else 0, _lib.ptr(parent), _lib.ptr(kofs), K, rows,
-               nd, tile)
+               nd, tile, layout)
         if self.static and rows < config.gpl_fixed_stride_max_rows:
             # static regime: one pass into fixed-stride slots, nothing to scan or read back
             cap = L.b200scn_gpl_max_groups(max(rows, 1), K, tile)
@@ -241,7 +246,7 @@ class Metadata(object):
             g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)
             _lib.call("b200scn_gpl_build", 2, *tab, _lib.ptr(tile_off), _lib.ptr(tile_end), None, _lib.ptr(g_rec), cap,
                       _lib.ptr(koff), None, 0, _stream())
-            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile, koff=koff,
+            return dict(tile_off=tile_off, tile_end=tile_end, g_rec=g_rec, K=K, tile_rows=tile, koff=koff, layout=layout,
                         rows_hint=config.gpl_rows_by_size.get(size_key, 0))
         total = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = L.b200scn_gpl_scratch_bytes(max(rows, 1))
@@ -255,16 +260,22 @@ class Metadata(object):
         g_rec = torch.empty(cap * 32, dtype=torch.int32, device=dev)  # [cap][8] int4 records
         _lib.call("b200scn_gpl_build", 1, *tab, _lib.ptr(tile_off), None, _lib.ptr(total), _lib.ptr(g_rec), cap,
                   _lib.ptr(koff), _lib.ptr(scratch), nbytes, _stream())
-        return dict(tile_off=tile_off, tile_end=None, g_rec=g_rec, K=K, tile_rows=tile, koff=koff,
+        return dict(tile_off=tile_off, tile_end=None, g_rec=g_rec, K=K, tile_rows=tile, koff=koff, layout=layout,
                     rows_hint=config.gpl_rows_by_size.get(size_key, 0) if self.static else 0)
 
-    def subm_gpl(self, spatial_size, filter_size):
-        self._note("subm_gpl", tuple(spatial_size), filter_size)
+    def subm_gpl(self, spatial_size, filter_size, layout=0):
+        """Pair list of the submanifold rules.  The layout-0 list carries `variant(layout)`, which hands out (and
+        builds on first use) the dense-first lists the large-input convolution kernel prefers."""
+        self._note("subm_gpl", tuple(spatial_size), filter_size, layout)
         lv = self.level(spatial_size)
-        key = ("subm", filter_size)
+        key = ("subm", filter_size) if layout == 0 else ("subm", filter_size, layout)
         if key not in lv.gpl:
             nbr = self.subm_table(spatial_size, filter_size)
-            lv.gpl[key] = self._build_gpl(lv, nbr, None, None, filter_size ** self.dimension, tuple(spatial_size))
+            gpl = self._build_gpl(lv, nbr, None, None, filter_size ** self.dimension, tuple(spatial_size), layout)
+            if layout == 0:
+                me, size = weakref.ref(self), tuple(spatial_size)
+                gpl["variant"] = lambda lay: me().subm_gpl(size, filter_size, lay)
+            lv.gpl[key] = gpl
         return lv.gpl[key]
 
     def strided_gpl(self, in_size, out_size, stride):
