@@ -40,7 +40,6 @@ namespace {
 constexpr int kMaxSmem = 220 * 1024;
 constexpr int kLargeWarps = 20;
 constexpr int kRecRing = 8;  // per-warp shared-memory ring of group records (128 B each)
-constexpr int kPfMax = 3;   // records this many groups ahead are guaranteed to have landed (L2 prefetch distance limit)
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // D(16 pairs x 8 co) += A(16 pairs x 8 ci) * B(8 ci x 8 co)
@@ -196,7 +195,6 @@ struct GplParams {
   int warps, split;  // split != 0: the CTA's warps share one tile
   uint32_t ones;     // 0xffffffff (opaque to the compiler)
   uint32_t zero;     // 0 (opaque to the compiler)
-  int pf;            // k_conv_gpl: L2 prefetch distance in groups (0 = off)
 };
 
 __device__ __forceinline__ float2 lds64(uint32_t a) {
@@ -247,8 +245,12 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 // latency once per loop trip (20% of all stall samples on one instruction).  Here the rows of group i + 1 are
 // requested right AFTER the first use of the rows of group i (their address carries a data dependence on a
 // loaded value, so ptxas cannot hoist them): every wait then only covers loads that are a whole group old.
-template <int Q, int MT, bool X3, bool D3, bool A128>
+template <int Q, int MT, bool X3, bool D3, bool A128, int NB>
 __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParams p) {
+  // NB: groups per batch.  The rows of a whole batch are requested together, right after the first use of the
+  // previous batch's rows: NB groups' gathers per warp in flight instead of one (the single scoreboard allows
+  // one wait per batch, see above) -- the kernel is bound by memory latency x bytes in flight.
+  static_assert(NB >= 1 && NB <= 3, "batch of 1..3 groups");
   // A128: accumulator rows in natural channel order, one LDS.128 / STS.128 per (row, 16 channels) -- half the
   // shared-memory wavefronts of the alternative, but the loaded quads hold two n-tiles of ONE row while an HMMA
   // accumulator quad holds one n-tile of TWO rows: 16 register moves per group.  !A128: n-tile j of a row is an
@@ -351,8 +353,8 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
     // (an async copy has no destination register, so ptxas cannot sink it next to its use the way it does
     // with plain loads).  Records and rows past the end of the range are clamped to the last group:
     // redundant but unconditional, never consumed.
-    float4 G[2][2][Q];
-    int Rz[2];
+    float4 G[2][NB][2][Q];
+    int Rz[2][NB];
     const int g_last = max(ge - 1, gb);
     const uint32_t ring_cp = s_ring + lane * 4, ring_rd = s_ring + g * 16;
     auto fetch_rec = [&](int grp) {  // lane l copies word l of the 128-byte record
@@ -364,9 +366,9 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
     // rows of group `grp` (its record must have landed in the ring) into register slot d; `dep` is zero, but
     // only at run time: it ties the request to the value it was derived from.  A negative input row (a missing
     // neighbour in a dense-first group) contributes zeros.
-    auto fetch_rows = [&](int grp, int d, uint32_t dep) {
+    auto fetch_rows = [&](int grp, int d, int bi, uint32_t dep) {
       const float4 r = lds128(ring_rd + (uint32_t)(grp & (kRecRing - 1)) * 128u);
-      Rz[d] = __float_as_int(r.z);
+      Rz[d][bi] = __float_as_int(r.z);
       const int i0 = __float_as_int(r.x), i1 = __float_as_int(r.y);
       if (D3) {
         const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)max(i0, 0) * ldb);
@@ -374,26 +376,32 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          G[d][0][q] = i0 >= 0 ? __ldg(s0 + 4 * q) : z4;
-          G[d][1][q] = i1 >= 0 ? __ldg(s1 + 4 * q) : z4;
+          G[d][bi][0][q] = i0 >= 0 ? __ldg(s0 + 4 * q) : z4;
+          G[d][bi][1][q] = i1 >= 0 ? __ldg(s1 + 4 * q) : z4;
         }
       } else {
         const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i0 * ldb);
         const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i1 * ldb);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          G[d][0][q] = __ldg(s0 + 4 * q);
-          G[d][1][q] = __ldg(s1 + 4 * q);
+          G[d][bi][0][q] = __ldg(s0 + 4 * q);
+          G[d][bi][1][q] = __ldg(s1 + 4 * q);
         }
       }
     };
+    // Record accounting: at the start of the batch that begins at group b0 the records up to b0 + kRecRing - 2
+    // have been requested; the batch requests NB more, and needs the NEXT batch's (up to b0 + 2 NB - 1) landed
+    // before it requests that batch's rows: at most kRecRing - 1 - NB request groups may still be pending.  (The
+    // new requests overwrite the ring slots of b0 - 1 .. b0 + NB - 2, whose fields were copied to registers when
+    // their rows were requested.)
     if (gb < ge) {
       __syncwarp();  // the previous tile's last ring reads are done
 #pragma unroll
       for (int u = 0; u < kRecRing - 1; ++u) fetch_rec(gb + u);
-      asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - kPfMax) : "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - NB) : "memory");
       __syncwarp();
-      fetch_rows(gb, 0, 0u);
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi) fetch_rows(gb + bi, 0, bi, 0u);
     }
 
     uint32_t wbh[WREG ? KS : 1][WREG ? MT : 1][4], wbl[WREG ? KS : 1][WREG ? MT : 1][4];
@@ -401,27 +409,25 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
     float dacc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) dacc[j][0] = dacc[j][1] = dacc[j][2] = dacc[j][3] = 0.f;
-    for (int g0 = gb; g0 < ge; g0 += 2) {
+    for (int g0 = gb; g0 < ge; g0 += 2 * NB) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int grp = g0 + u;
-        if (grp >= ge) break;
+        const int b0 = g0 + u * NB;
+        if (b0 >= ge) break;
         const int d = u;
-        fetch_rec(grp + kRecRing - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - kPfMax) : "memory");  // records up to grp + kPfMax have landed
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) fetch_rec(b0 + bi + kRecRing - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 1 - NB) : "memory");
         __syncwarp();
-        // first use of this group's rows, then the request for the next group's
-        const uint32_t dep = __float_as_uint(G[d][0][0].x) & p.zero;
-        fetch_rows(grp + 1, d ^ 1, dep);
-        if (p.pf) {
-          // rows of a group further ahead: L2 prefetch (no destination register, hence no scoreboard) -- turns
-          // the DRAM misses among them (60% of the gathers miss L2) into L2 hits by the time they are requested
-          const float4 r = lds128(ring_rd + (uint32_t)((grp + p.pf) & (kRecRing - 1)) * 128u);
-          const int i0 = __float_as_int(r.x), i1 = __float_as_int(r.y);
-          if (!D3 || i0 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_l + (uint64_t)(uint32_t)i0 * ldb));
-          if (!D3 || i1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_l + (uint64_t)(uint32_t)i1 * ldb));
-        }
-        const uint32_t mz = (uint32_t)Rz[d];
+        // first use of this batch's rows, then the request for the next batch's
+        const uint32_t dep = __float_as_uint(G[d][0][0][0].x) & p.zero;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) fetch_rows(b0 + NB + bi, d ^ 1, bi, dep);
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) {
+        const int grp = b0 + bi;
+        if (grp >= ge) break;
+        const uint32_t mz = (uint32_t)Rz[d][bi];
         const int kk = (mz >> 16) & 0xff, fl = (int)(mz >> 24);
         const int o0 = mz & 0xff, o1 = (mz >> 8) & 0xff;
         // C operand: the running sums of the 16 output rows
@@ -462,8 +468,8 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float f0[4] = {G[d][0][q].x, G[d][0][q].y, G[d][0][q].z, G[d][0][q].w};
-          const float f1[4] = {G[d][1][q].x, G[d][1][q].y, G[d][1][q].z, G[d][1][q].w};
+          const float f0[4] = {G[d][bi][0][q].x, G[d][bi][0][q].y, G[d][bi][0][q].z, G[d][bi][0][q].w};
+          const float f1[4] = {G[d][bi][1][q].x, G[d][bi][1][q].y, G[d][bi][1][q].z, G[d][bi][1][q].w};
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int s = 2 * q + h;
@@ -527,6 +533,7 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
           }
         }
         __syncwarp();
+        }
       }
     }
 
@@ -769,11 +776,11 @@ int large_warps() {
 }
 
 // ---- large inputs: k_conv_gpl, one warp per tile, weights resident in shared memory ---------------
-template <int Q, int MT, bool X3, bool D3, bool A128>
+template <int Q, int MT, bool X3, bool D3, bool A128, int NB>
 int launch_large(GplParams p, int passes, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, X3, D3, A128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, X3, D3, A128, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kMaxSmem));
     configured = true;
   }
@@ -783,42 +790,45 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   while (warps > 1 && fixed + warps * per_warp > (size_t)kMaxSmem) --warps;
   p.warps = warps;
   p.split = 0;
-  static int pf = -1;  // B200SCN_GPL_PF: L2 prefetch distance in groups, 0 = off, at most kPfMax (A/B runs)
-  if (pf < 0) {
-    const char* e = getenv("B200SCN_GPL_PF");
-    pf = e ? atoi(e) : 0;
-    if (pf < 0 || pf > kPfMax) pf = 0;
-  }
-  p.pf = pf;
   const int64_t tiles = cdiv(p.n_cap, 128);
   int64_t gx = cdiv(tiles, warps);
   int64_t gmax = sm_count() / passes;
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  launch_pdl(k_conv_gpl<Q, MT, X3, D3, A128>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
+  launch_pdl(k_conv_gpl<Q, MT, X3, D3, A128, NB>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
 }
 
+// groups per batch: 2 by default where the rows of two batches fit the register budget; B200SCN_GPL_BATCH = 1 / 2 / 3
+// overrides it for the 16 -> 16 tf32x3 instantiation (A/B runs)
 template <int Q>
 int launch_large_q(const GplParams& p, int MT, int passes, int x3, int d3, cudaStream_t st) {
-  static int a128 = -1;  // B200SCN_GPL_ACC128 = 0 / 1: accumulator access width (A/B runs)
+  static int a128 = -1, nb = -1;  // B200SCN_GPL_ACC128 = 0 / 1: accumulator access width (A/B runs)
   if (a128 < 0) {
     const char* e = getenv("B200SCN_GPL_ACC128");
     a128 = e ? (atoi(e) != 0) : 1;
+    e = getenv("B200SCN_GPL_BATCH");
+    nb = e ? atoi(e) : 2;
+    if (nb < 1 || nb > 3) nb = 2;
   }
+  constexpr int NBQ = Q == 1 ? 2 : 1;  // wider rows: two batches' rows no longer fit the register budget
   if (d3) {  // layout-3 lists (A/B runs): tf32x3 only
-    if (MT == 1) return launch_large<Q, 1, true, true, true>(p, passes, st);
-    return launch_large<Q, 2, true, true, true>(p, passes, st);
+    if (MT == 1) return launch_large<Q, 1, true, true, true, NBQ>(p, passes, st);
+    return launch_large<Q, 2, true, true, true, NBQ>(p, passes, st);
   }
-  if (!a128 && x3) {
-    if (MT == 1) return launch_large<Q, 1, true, false, false>(p, passes, st);
-    return launch_large<Q, 2, true, false, false>(p, passes, st);
+  if constexpr (Q == 1) {
+    if (MT == 1 && x3) {
+      if (!a128) return launch_large<Q, 1, true, false, false, 2>(p, passes, st);
+      if (nb == 1) return launch_large<Q, 1, true, false, true, 1>(p, passes, st);
+      if (nb == 3) return launch_large<Q, 1, true, false, true, 3>(p, passes, st);
+      return launch_large<Q, 1, true, false, true, 2>(p, passes, st);
+    }
   }
-  if (MT == 1) return x3 ? launch_large<Q, 1, true, false, true>(p, passes, st) : launch_large<Q, 1, false, false, true>(p, passes, st);
-  return x3 ? launch_large<Q, 2, true, false, true>(p, passes, st) : launch_large<Q, 2, false, false, true>(p, passes, st);
+  if (MT == 1) return x3 ? launch_large<Q, 1, true, false, true, NBQ>(p, passes, st) : launch_large<Q, 1, false, false, true, NBQ>(p, passes, st);
+  return x3 ? launch_large<Q, 2, true, false, true, NBQ>(p, passes, st) : launch_large<Q, 2, false, false, true, NBQ>(p, passes, st);
 }
 
 // ---- small inputs: k_conv_gpl_small ---------------------------------------------------------------
@@ -1069,7 +1079,7 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   p.tile_off = tile_off; p.tile_end = tile_end; p.g_rec = reinterpret_cast<const int4*>(g_rec); p.Q = Cin / 16;
   p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = accumulate;
   p.res = res; p.ldr = (int)ldr;
-  p.warps = 8; p.split = 1; p.ones = 0xffffffffu; p.zero = 0u; p.pf = 0;
+  p.warps = 8; p.split = 1; p.ones = 0xffffffffu; p.zero = 0u;
 
   const int MTL = large_pass_width(tile_rows, tile_end == nullptr, n_out_cap, Cin, Cout, K, x3);
   B200_CHECK_ARG(layout != 3 || x3, "conv_gpl: layout-3 pair lists are served in the tf32x3 mode only");
