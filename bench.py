@@ -544,18 +544,35 @@ def run_b200(args):
     print(json.dumps(line))
 
 
+def _own_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write banners to file descriptor 1 behind Python's back
+    (NCCL prints "NCCL version ..." there when the first communicator is created).  Python's sys.stdout keeps the
+    real stdout; descriptor 1 itself is pointed at stderr for everything else in the process."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
     args = parse()
+    _own_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    # Every rank has passed the final barrier of run_b200 by now.  No NCCL teardown: ncclCommDestroy waits for every
+    # CUDA graph that captured the communicator's kernels (tests/test_gpu_trainer.py met that hang), and nothing
+    # is gained by an orderly teardown of a process that is about to exit.
+    sys.stdout.flush()
+    sys.stderr.flush()
     try:
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     except Exception:
-        pass
+        multi = False
+    if multi:
+        os._exit(0)
 
 
 if __name__ == "__main__":
