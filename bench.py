@@ -291,16 +291,50 @@ def subm_roofline(args, math_mode):
     t = statistics.mean(times)
     # algorithmic bytes: s*(N*Cin + N*Cout) + 4*K*N + s*K*Cin*Cout
     alg = 4 * (n * C + n * C) + 4 * K * n + 4 * K * C * C
-    peak, src = peaks()
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch, from ncu --set full
     if os.path.exists(tpath) and args.roofline_events == 128:
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj.get("subm16_fwd_bytes_per_launch"), tj.get("source")
+    # the rulebook work behind that launch, same workload (north star, job 1): active-site hash table + row order,
+    # 3^3 neighbour table, grouped pair list -- each timed as a whole call (CUDA events, best of 3 fresh builds, L2
+    # flushed; the input build includes its one 8-byte read-back), against its algorithmic bytes
+    def timed(fn):
+        best = None
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            r = fn()
+            e1.record(st)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best, r
+
+    peak, src = peaks()
+    rb = {}
+    try:
+        t_in, _ = timed(lambda: Metadata(3).set_input(coords, size))
+        md2 = Metadata(3)
+        md2.set_input(coords, size)
+        t_tab, _ = timed(lambda: (md2.levels[size].subm.clear(), md2.subm_table(size, 3)))
+        lay = gpl["layout"] if use_gpl else 0
+        t_gpl, _ = timed(lambda: (md2.levels[size].gpl.clear(), md2.subm_gpl(size, 3, lay)))
+        n_in = coords.shape[0]
+        for name, ms, nbytes in (("input_build (hash insert, first-occurrence row order, duplicate CSR)", t_in,
+                                  8 * 4 * n_in + 16 * 2 * n_in + 8 * n + 12 * n_in),
+                                 ("subm_table (3^3 neighbour table)", t_tab, 8 * n + 4 * K * n),
+                                 ("gpl_build (count + scan + fill, layout %d)" % lay, t_gpl,
+                                  2 * 4 * K * n + (gpl["g_rec"].numel() * 4 if use_gpl else 0))):
+            rb[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GB/s": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+        del md2
+    except Exception as e:  # never lose the conv number over the side measurement
+        rb = {"error": repr(e)}
     del flush
     torch.cuda.empty_cache()
-    return {"bound": "hbm", "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
+    return {"bound": "hbm", "achieved": alg / t / 1e9, "rulebook": rb, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "kernel": ("b200scn_conv_gpl" if use_gpl else "b200scn_conv_table") + " (subm 3^3, 16->16, fwd)",
             "workload": "%d events of 512^3 concatenated: %d active sites, %d rule pairs (working set > L2)"
                         % (args.roofline_events, n, pairs),

@@ -112,12 +112,11 @@ int b200scn_subm_table(const uint64_t* ukeys, int64_t n_cap, const int32_t* n_de
  * koff (optional, stages 1 and 2): int32[tiles * (K + 1)], first group of every offset inside each tile
  * (entry K = end of the tile) -- the index b200scn_wgrad_gpl walks.
  * layout: 0 = every offset's pairs compacted into groups, offsets ascending (what every kernel reads).
- *         1 / 3 = dense-first, submanifold tables only, no koff: the centre offset (1), or the centre and its two
- *         neighbours along the last axis (3), come first as one group per 16-row sub-tile whose slot j IS output
- *         row 16 s + j (input row -1 where the neighbour is missing); byte 3 of word 2 carries flags telling
- *         the large-input kernel to keep that sub-tile's sums in registers across those groups (1: C = 0,
- *         2: do not store D, 4: C = previous D).  The other offsets follow as in layout 0.  Only the
- *         large-input kernel of b200scn_conv_gpl reads these lists: ask b200scn_conv_gpl_layout. */
+ *         1 = centre first, submanifold tables only, no koff: the centre offset comes first as one group per 16-row
+ *         sub-tile whose slot j IS output row 16 s + j; byte 3 of word 2 carries flag 1 ("C = 0"), telling the
+ *         large-input kernel to start that sub-tile's sums in registers instead of reading its accumulator.  The
+ *         other offsets follow as in layout 0.  Only the large-input kernel of b200scn_conv_gpl reads these
+ *         lists: ask b200scn_conv_gpl_layout. */
 int b200scn_gpl_tile_rows(int64_t n); /* recommended tile_rows for a level of n rows */
 int64_t b200scn_gpl_max_groups(int64_t n_cap, int K, int tile_rows);
 int64_t b200scn_gpl_scratch_bytes(int64_t n_cap);
@@ -151,8 +150,8 @@ int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, const float* 
                      int Cout, float* out, int64_t ldo, int accumulate, const float* res, int64_t ldr, int math_mode,
                      void* stream);
 
-/* layout (b200scn_gpl_build) the convolution of these shapes wants its pair list in: 0, or a dense-first
- * code when the large-input kernel will run (scanned != 0: lists with scanned tile offsets, i.e. tile_end == NULL;
+/* layout (b200scn_gpl_build) the convolution of these shapes wants its pair list in: 0, or 1 (centre first)
+ * when the large-input kernel will run (scanned != 0: lists with scanned tile offsets, i.e. tile_end == NULL;
  * submanifold != 0: the list comes from a submanifold neighbour table). */
 int b200scn_conv_gpl_layout(int tile_rows, int scanned, int64_t n_out_cap, int Cin, int Cout, int K, int submanifold,
                             int math_mode);

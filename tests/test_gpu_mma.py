@@ -171,12 +171,12 @@ def test_gpl_and_pairs_kernels_agree(mode):
     assert (a - b).abs().max().item() <= (1e-5 if mode == 1 else 2e-3) * a.abs().max().item()
 
 
-@pytest.mark.parametrize("mode,cin,cout,layout", [(1, 16, 16, 0), (1, 16, 16, 1), (1, 16, 16, 3), (2, 16, 16, 3),
-                                                  (1, 64, 32, 3), (1, 32, 32, 3), (2, 32, 64, 1)])
+@pytest.mark.parametrize("mode,cin,cout,layout", [(1, 16, 16, 0), (1, 16, 16, 1), (2, 16, 16, 1), (1, 64, 32, 1),
+                                                  (1, 32, 32, 1), (1, 16, 32, 1), (2, 32, 64, 1)])
 def test_large_input_gpl_kernel(mode, cin, cout, layout):
     """k_conv_gpl (one warp per 128-row tile, weights resident in shared memory -- the kernel bench.py's
-    roofline times) against the neighbour-table kernel, for the three pair-list layouts (offset-major, centre
-    first, centre + last-axis neighbours first); then the module path (SubmanifoldConvolution forward, dgrad and
+    roofline times) against the neighbour-table kernel, for both pair-list layouts (offset-major, centre first);
+    then the module path (SubmanifoldConvolution forward, dgrad and
     wgrad with the list variant functional._conv_gpl picks) against the FFMA mode.  Runs in a subprocess because
     the row threshold that selects the kernel is read once per process (B200SCN_GPL_LARGE_MIN_ROWS)."""
     import subprocess
@@ -202,10 +202,9 @@ x = torch.randn(n, Cin, device="cuda"); W = torch.randn(K, Cin, Cout, device="cu
 st = torch.cuda.current_stream().cuda_stream
 served = 0
 for (si, so, flip, ci, co) in ((Cout, 1, 0, Cin, Cout), (1, Cout, 1, Cout, Cin)):
-    # what the library serves for this direction: 0 = not the large-input kernel (shared-memory budget), else the
-    # dense-first lists (layout 3 in the tf32x3 mode only)
+    # what the library serves for this direction: 0 = not the large-input kernel (shared-memory budget)
     want = _lib.load().b200scn_conv_gpl_layout(128, 1, n, ci, co, K, 1, mode)
-    lay = 0 if want == 0 else (1 if (layout == 3 and mode == 2) else layout)
+    lay = 0 if want == 0 else layout
     served += want != 0
     gpl = md.subm_gpl(size, 3, lay)
     assert gpl["tile_rows"] == 128 and gpl["tile_end"] is None and gpl["layout"] == lay

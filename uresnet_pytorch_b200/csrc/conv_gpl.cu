@@ -50,10 +50,8 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Record flags (byte 3 of word 2), set by the builder's dense-first layouts and read by k_conv_gpl
+// Record flags (byte 3 of word 2), set by the builder's centre-first layout and read by k_conv_gpl
 constexpr int kGplCZero = 1;    // C = 0 (first group of a sub-tile: nothing to read)
-constexpr int kGplNoStore = 2;  // D stays in registers (the next group continues the same sub-tile)
-constexpr int kGplCKeep = 4;    // C = the previous group's D (still in registers)
 
 // ---- builder -------------------------------------------------------------------------------------
 // one warp per tile; FILL == false: count groups per tile; FILL == true: write the records
@@ -64,13 +62,12 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
                             int32_t* __restrict__ tile_beg_out, int4* __restrict__ g_rec, int64_t cap_groups,
                             int32_t* __restrict__ koff, int layout) {
   constexpr int NR = R / 32;  // rows per lane
-  // dense-first layouts (submanifold tables only): the centre offset (layout 1), or the centre and the two
-  // neighbours along the last axis (layout 3), are listed FIRST and per 16-row sub-tile -- slot j of such a
-  // group is output row 16 s + j whether or not the neighbour exists (input row -1 = none) -- so that the
-  // convolution kernel keeps the sub-tile's sums in registers across them (flags, see k_conv_gpl)
+  // centre-first layout (layout 1, submanifold tables only): the centre offset is listed FIRST and per 16-row
+  // sub-tile -- slot j of such a group is output row 16 s + j -- so that the convolution kernel starts the
+  // sub-tile's sums in registers instead of reading the shared-memory accumulator (flag kGplCZero, see k_conv_gpl)
   const int kc = (K - 1) >> 1;
-  const int nd = (table != nullptr && parent == nullptr) ? (layout == 3 ? 3 : (layout == 1 ? 1 : 0)) : 0;
-  const int kd0 = kc - (nd >> 1);  // first dense offset
+  const int nd = (table != nullptr && parent == nullptr && layout == 1) ? 1 : 0;
+  const int kd0 = kc;  // the dense offset
   const int n = live_rows(n_dev, n_cap);
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
@@ -106,12 +103,12 @@ __global__ void k_gpl_build(const int32_t* __restrict__ table, int64_t ld, const
         int32_t* rec = reinterpret_cast<int32_t*>(g_rec + grp * 8);
         for (int dk = 0; dk < nd; ++dk) {
           const int k = kd0 + dk;
-          const int flags = (dk == 0 ? kGplCZero : kGplCKeep) | (dk + 1 < nd ? kGplNoStore : 0);
+          const int flags = kGplCZero;
 #pragma unroll
           for (int i = 0; i < NR; ++i) {
             const int r = base + 32 * i + lane;
-            // (layout 1: the centre "neighbour" always exists; rows past the end read row 0 into sums nobody stores)
-            const int in_row = r < n ? __ldg(table + (int64_t)k * ld + r) : (nd == 1 ? 0 : -1);
+            // (the centre "neighbour" always exists; rows past the end read row 0 into sums nobody stores)
+            const int in_row = r < n ? __ldg(table + (int64_t)k * ld + r) : 0;
             const int st = 2 * i + (lane >> 4), j = lane & 15;  // sub-tile, slot
             int32_t* ent = rec + ((st * nd + dk) * 8 + (j & 7)) * 4;
             ent[j >> 3] = in_row;
@@ -222,9 +219,9 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-// Dense-first groups (record flags, byte 3 of word 2): the group's 16 slots are the 16 consecutive output rows
-// of one sub-tile, so its running sums stay in the MMA accumulator registers from one group to the next
-// instead of going through the shared-memory accumulator.
+// Centre-first groups (record flag kGplCZero, byte 3 of word 2): the group's 16 slots are the 16 consecutive
+// output rows of one sub-tile and the centre offset is the first one listed, so the sub-tile's sums START in the
+// MMA accumulator registers (C = 0) instead of being read from the zero-filled shared-memory accumulator.
 
 // Large inputs.  Q = Cin / 16, MT = output channels of this pass / 16, X3: 3-term tf32 split.  One warp per
 // 128-row tile; all K weight slices resident in shared memory in fragment order.
@@ -239,24 +236,19 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 // pass (128 B) swap their 64-byte halves on odd rows, so that the two rows a quarter-warp touches in one
 // shared-memory wavefront collide only when their parities are equal (the same rule as for 64-byte rows).
 //
-// Pipeline (profiles/README.md, round 2): ptxas tracks ALL row gathers of a warp on one scoreboard, and a
+// Pipeline (profiles/README.md section 0.3): ptxas tracks ALL row gathers of a warp on one scoreboard, and a
 // wait on a scoreboard waits for every load on it -- so the first use of a group's rows also waits for
-// whatever was requested after them.  With rows requested two groups ahead this exposed the full memory
-// latency once per loop trip (20% of all stall samples on one instruction).  Here the rows of group i + 1 are
-// requested right AFTER the first use of the rows of group i (their address carries a data dependence on a
-// loaded value, so ptxas cannot hoist them): every wait then only covers loads that are a whole group old.
-template <int Q, int MT, bool X3, bool D3, bool A128, int NB>
+// whatever was requested after them.  With rows requested two groups ahead (round 1) this exposed the full
+// memory latency once per loop trip (20% of all stall samples on one instruction).  Here the rows of the next
+// BATCH of NB groups are requested right AFTER the first use of the current batch's rows (their address carries
+// a data dependence on a loaded value, so ptxas cannot hoist them): every wait then only covers loads that are
+// a whole batch old, and NB groups' rows per warp are in flight -- the kernel is bound by memory latency x
+// bytes in flight first (0.321 -> 0.297 ms from NB = 1 to 2), by the L1/shared data pipe next (74% busy).
+// Measured and rejected: rows through a cp.async shared-memory ring (removes the latency stalls, adds 20
+// wavefronts per group: 0.344 ms; L1-bypassing copies 1.1 ms), prefetch.global.L2 (0.8 ms), NB = 3 (spills).
+template <int Q, int MT, bool X3, int NB>
 __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParams p) {
-  // NB: groups per batch.  The rows of a whole batch are requested together, right after the first use of the
-  // previous batch's rows: NB groups' gathers per warp in flight instead of one (the single scoreboard allows
-  // one wait per batch, see above) -- the kernel is bound by memory latency x bytes in flight.
   static_assert(NB >= 1 && NB <= 3, "batch of 1..3 groups");
-  // A128: accumulator rows in natural channel order, one LDS.128 / STS.128 per (row, 16 channels) -- half the
-  // shared-memory wavefronts of the alternative, but the loaded quads hold two n-tiles of ONE row while an HMMA
-  // accumulator quad holds one n-tile of TWO rows: 16 register moves per group.  !A128: n-tile j of a row is an
-  // 8-byte piece, LDS.64 / STS.64 straight into / out of the accumulator quads (column map: co = 8j + 2t (+1)).
-  // D3: the list may hold layout-3 groups (missing neighbours as input row -1, sums kept in registers across
-  // groups); otherwise only "C = 0" groups (layout 1) need support
   constexpr int R = 128, KS = 2 * Q, CT = 16 * MT, C4 = CT / 4, NT = 2 * MT;
   // WREG: the B fragments of the current offset live in registers and are reloaded (raw fp32 from shared
   // memory, low parts recomputed) only when the offset changes -- the L1/shared data pipe is this
@@ -298,8 +290,7 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
       const int c16 = ci & 15, tt = c16 >> 2, rem = c16 & 3;
       const int s = ((ci >> 4) << 1) + (rem >> 1);
       const int mt = col >> 4;
-      const int jj = A128 ? (col >> 1) & 1 : (col >> 3) & 1;
-      const int gg = A128 ? ((((col & 15) >> 2) << 1) | (col & 1)) : (col & 7);
+      const int jj = (col >> 1) & 1, gg = (((col & 15) >> 2) << 1) | (col & 1);
       const int dst = ((((k * KS + s) * MT + mt) * 32) + gg * 4 + tt) * 4 + jj * 2 + (rem & 1);
       Whi[dst] = v;  // raw fp32: the tensor core truncates the high part itself, the low part is recomputed
     }
@@ -336,12 +327,6 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
     const int chunk = (4 * mt + t) ^ ((MT == 2) ? ((row & 1) << 2) : 0);
     return s_acc + (uint32_t)row * (CT * 4) + (uint32_t)chunk * 16u;
   };
-  // !A128: 8-channel piece j of a row sits at position j ^ x(row), x = (row >> 1) & 1 (MT odd) or row & 3 (MT
-  // even), so that the LDS.64 / STS.64 of four consecutive rows fall into distinct banks
-  auto acc_addr64 = [&](int row, int j) -> uint32_t {
-    const int x = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
-    return s_acc + (uint32_t)row * (CT * 4) + (uint32_t)((j ^ x) << 5) + (uint32_t)t * 8u;
-  };
   for (int64_t wt = wt_begin; wt < wt_end; ++wt) {
     const int base = (int)(wt * R);
     __syncwarp();
@@ -364,29 +349,17 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // rows of group `grp` (its record must have landed in the ring) into register slot d; `dep` is zero, but
-    // only at run time: it ties the request to the value it was derived from.  A negative input row (a missing
-    // neighbour in a dense-first group) contributes zeros.
+    // only at run time: it ties the request to the value it was derived from.
     auto fetch_rows = [&](int grp, int d, int bi, uint32_t dep) {
       const float4 r = lds128(ring_rd + (uint32_t)(grp & (kRecRing - 1)) * 128u);
       Rz[d][bi] = __float_as_int(r.z);
       const int i0 = __float_as_int(r.x), i1 = __float_as_int(r.y);
-      if (D3) {
-        const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)max(i0, 0) * ldb);
-        const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)max(i1, 0) * ldb);
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i0 * ldb);
+      const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i1 * ldb);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          G[d][bi][0][q] = i0 >= 0 ? __ldg(s0 + 4 * q) : z4;
-          G[d][bi][1][q] = i1 >= 0 ? __ldg(s1 + 4 * q) : z4;
-        }
-      } else {
-        const float4* s0 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i0 * ldb);
-        const float4* s1 = reinterpret_cast<const float4*>(in_l + dep + (uint64_t)(uint32_t)i1 * ldb);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          G[d][bi][0][q] = __ldg(s0 + 4 * q);
-          G[d][bi][1][q] = __ldg(s1 + 4 * q);
-        }
+      for (int q = 0; q < Q; ++q) {
+        G[d][bi][0][q] = __ldg(s0 + 4 * q);
+        G[d][bi][1][q] = __ldg(s1 + 4 * q);
       }
     };
     // Record accounting: at the start of the batch that begins at group b0 the records up to b0 + kRecRing - 2
@@ -434,20 +407,12 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
         if (fl & kGplCZero) {
 #pragma unroll
           for (int j = 0; j < NT; ++j) dacc[j][0] = dacc[j][1] = dacc[j][2] = dacc[j][3] = 0.f;
-        } else if (!D3 || !(fl & kGplCKeep)) {
-          if (A128) {
+        } else {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const float4 c0 = lds128(acc_addr(o0, mt)), c1 = lds128(acc_addr(o1, mt));
-              dacc[2 * mt][0] = c0.x; dacc[2 * mt][1] = c0.y; dacc[2 * mt + 1][0] = c0.z; dacc[2 * mt + 1][1] = c0.w;
-              dacc[2 * mt][2] = c1.x; dacc[2 * mt][3] = c1.y; dacc[2 * mt + 1][2] = c1.z; dacc[2 * mt + 1][3] = c1.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-              const float2 c01 = lds64(acc_addr64(o0, j)), c23 = lds64(acc_addr64(o1, j));
-              dacc[j][0] = c01.x; dacc[j][1] = c01.y; dacc[j][2] = c23.x; dacc[j][3] = c23.y;
-            }
+          for (int mt = 0; mt < MT; ++mt) {
+            const float4 c0 = lds128(acc_addr(o0, mt)), c1 = lds128(acc_addr(o1, mt));
+            dacc[2 * mt][0] = c0.x; dacc[2 * mt][1] = c0.y; dacc[2 * mt + 1][0] = c0.z; dacc[2 * mt + 1][1] = c0.w;
+            dacc[2 * mt][2] = c1.x; dacc[2 * mt][3] = c1.y; dacc[2 * mt + 1][2] = c1.z; dacc[2 * mt + 1][3] = c1.w;
           }
         }
         const uint32_t wk_off = (uint32_t)kk * (KS * MT * 512);
@@ -517,20 +482,10 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
             }
           }
         }
-        if (!D3 || !(fl & kGplNoStore)) {
-          if (A128) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              sts128(acc_addr(o0, mt), dacc[2 * mt][0], dacc[2 * mt][1], dacc[2 * mt + 1][0], dacc[2 * mt + 1][1]);
-              sts128(acc_addr(o1, mt), dacc[2 * mt][2], dacc[2 * mt][3], dacc[2 * mt + 1][2], dacc[2 * mt + 1][3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-              sts64(acc_addr64(o0, j), dacc[j][0], dacc[j][1]);
-              sts64(acc_addr64(o1, j), dacc[j][2], dacc[j][3]);
-            }
-          }
+        for (int mt = 0; mt < MT; ++mt) {
+          sts128(acc_addr(o0, mt), dacc[2 * mt][0], dacc[2 * mt][1], dacc[2 * mt + 1][0], dacc[2 * mt + 1][1]);
+          sts128(acc_addr(o1, mt), dacc[2 * mt][2], dacc[2 * mt][3], dacc[2 * mt + 1][2], dacc[2 * mt + 1][3]);
         }
         __syncwarp();
         }
@@ -541,13 +496,7 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
     for (int e = lane; e < R * C4; e += 32) {
       const int row = e / C4, c4 = e - row * C4;
       if (base + row < n) {
-        int src;
-        if (A128) {
-          src = row * C4 + (c4 ^ ((MT == 2) ? ((row & 1) << 2) : 0));
-        } else {
-          const int xr = (MT & 1) ? ((row >> 1) & 1) : (row & 3);
-          src = row * C4 + ((((c4 >> 1) ^ xr) << 1) | (c4 & 1));
-        }
+        const int src = row * C4 + (c4 ^ ((MT == 2) ? ((row & 1) << 2) : 0));
         float4 v = acc[src];
         float* o = p.out + (int64_t)(base + row) * p.ldo + cob + 4 * c4;
         if (p.res != nullptr) {
@@ -776,11 +725,11 @@ int large_warps() {
 }
 
 // ---- large inputs: k_conv_gpl, one warp per tile, weights resident in shared memory ---------------
-template <int Q, int MT, bool X3, bool D3, bool A128, int NB>
+template <int Q, int MT, bool X3, int NB>
 int launch_large(GplParams p, int passes, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, X3, D3, A128, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(k_conv_gpl<Q, MT, X3, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kMaxSmem));
     configured = true;
   }
@@ -796,39 +745,18 @@ int launch_large(GplParams p, int passes, cudaStream_t st) {
   if (gmax < 1) gmax = 1;
   if (gx > gmax) gx = gmax;
   dim3 grid((unsigned)gx, (unsigned)passes);
-  launch_pdl(k_conv_gpl<Q, MT, X3, D3, A128, NB>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
+  launch_pdl(k_conv_gpl<Q, MT, X3, NB>, grid, dim3(warps * 32), fixed + warps * per_warp, st, p);
   count_launches(1);
   B200_CHECK_LAUNCH("conv_gpl");
   return 0;
 }
 
-// groups per batch: 2 by default where the rows of two batches fit the register budget; B200SCN_GPL_BATCH = 1 / 2 / 3
-// overrides it for the 16 -> 16 tf32x3 instantiation (A/B runs)
+// groups per batch: 2 where the rows of two batches fit the register budget (16 -> 16 channel passes), else 1
 template <int Q>
-int launch_large_q(const GplParams& p, int MT, int passes, int x3, int d3, cudaStream_t st) {
-  static int a128 = -1, nb = -1;  // B200SCN_GPL_ACC128 = 0 / 1: accumulator access width (A/B runs)
-  if (a128 < 0) {
-    const char* e = getenv("B200SCN_GPL_ACC128");
-    a128 = e ? (atoi(e) != 0) : 1;
-    e = getenv("B200SCN_GPL_BATCH");
-    nb = e ? atoi(e) : 2;
-    if (nb < 1 || nb > 3) nb = 2;
-  }
-  constexpr int NBQ = Q == 1 ? 2 : 1;  // wider rows: two batches' rows no longer fit the register budget
-  if (d3) {  // layout-3 lists (A/B runs): tf32x3 only
-    if (MT == 1) return launch_large<Q, 1, true, true, true, NBQ>(p, passes, st);
-    return launch_large<Q, 2, true, true, true, NBQ>(p, passes, st);
-  }
-  if constexpr (Q == 1) {
-    if (MT == 1 && x3) {
-      if (!a128) return launch_large<Q, 1, true, false, false, 2>(p, passes, st);
-      if (nb == 1) return launch_large<Q, 1, true, false, true, 1>(p, passes, st);
-      if (nb == 3) return launch_large<Q, 1, true, false, true, 3>(p, passes, st);
-      return launch_large<Q, 1, true, false, true, 2>(p, passes, st);
-    }
-  }
-  if (MT == 1) return x3 ? launch_large<Q, 1, true, false, true, NBQ>(p, passes, st) : launch_large<Q, 1, false, false, true, NBQ>(p, passes, st);
-  return x3 ? launch_large<Q, 2, true, false, true, NBQ>(p, passes, st) : launch_large<Q, 2, false, false, true, NBQ>(p, passes, st);
+int launch_large_q(const GplParams& p, int MT, int passes, int x3, cudaStream_t st) {
+  constexpr int NB = Q == 1 ? 2 : 1;
+  if (MT == 1) return x3 ? launch_large<Q, 1, true, NB>(p, passes, st) : launch_large<Q, 1, false, NB>(p, passes, st);
+  return x3 ? launch_large<Q, 2, true, 1>(p, passes, st) : launch_large<Q, 2, false, 1>(p, passes, st);
 }
 
 // ---- small inputs: k_conv_gpl_small ---------------------------------------------------------------
@@ -972,9 +900,9 @@ extern "C" int b200scn_gpl_build(int stage, const int32_t* table, int64_t ld, co
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= 64, "gpl_build: K must be 1..64");
   B200_CHECK_ARG(tile_rows == 32 || tile_rows == 64 || tile_rows == 128, "gpl_build: tile_rows must be 32, 64 or 128");
-  B200_CHECK_ARG(layout == 0 || ((layout == 1 || layout == 3) && table != nullptr && parent == nullptr && (K & 1) &&
-                                 K >= 3 && koff == nullptr),
-                 "gpl_build: dense-first layouts (1, 3) need a submanifold table with an odd offset count and no koff");
+  B200_CHECK_ARG(layout == 0 || (layout == 1 && table != nullptr && parent == nullptr && (K & 1) && K >= 3 &&
+                                 koff == nullptr),
+                 "gpl_build: the centre-first layout (1) needs a submanifold table with an odd offset count and no koff");
   B200_CHECK_ARG(stage == 2 || scratch_bytes >= b200scn_gpl_scratch_bytes(n_cap), "gpl_build: scratch too small");
   const int64_t tiles = cdiv(n_cap < 1 ? 1 : n_cap, tile_rows);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(scratch);
@@ -1030,20 +958,18 @@ static int large_pass_width(int tile_rows, bool scanned, int64_t n_out_cap, int 
 }
 
 /* Pair-list layout the convolution of these shapes wants (b200scn_gpl_build's `layout`): 0 = offset-major groups
- * only (every kernel reads it), 1 / 3 = dense-first (the large-input kernel only).  B200SCN_GPL_DENSE overrides
- * the dense-first choice (0 / 1 / 3, A/B runs). */
+ * only (every kernel reads it), 1 = centre offset first (the large-input kernel only).  B200SCN_GPL_DENSE=0 turns
+ * the centre-first choice off (A/B runs). */
 extern "C" int b200scn_conv_gpl_layout(int tile_rows, int scanned, int64_t n_out_cap, int Cin, int Cout, int K,
                                        int submanifold, int math_mode) {
   static int dense = -1;
   if (dense < 0) {
     const char* e = getenv("B200SCN_GPL_DENSE");
-    dense = e ? atoi(e) : 1;
-    if (dense != 0 && dense != 1 && dense != 3) dense = 1;
+    dense = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (!submanifold || !(K & 1) || K < 3 || Cin % 16 || Cout % 16) return 0;
   const int x3 = math_mode == B200SCN_MATH_TF32X3 ? 1 : 0;
-  if (!large_pass_width(tile_rows, scanned != 0, n_out_cap, Cin, Cout, K, x3)) return 0;
-  return (dense == 3 && !x3) ? 1 : dense;
+  return large_pass_width(tile_rows, scanned != 0, n_out_cap, Cin, Cout, K, x3) ? dense : 0;
 }
 
 extern "C" int b200scn_pack_weights(const int64_t* jobs_dev, int n_jobs, int64_t max_elems, void* stream) {
@@ -1085,13 +1011,13 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   B200_CHECK_ARG(layout != 3 || x3, "conv_gpl: layout-3 pair lists are served in the tf32x3 mode only");
   if (MTL) {
     switch (p.Q) {
-      case 1: return launch_large_q<1>(p, MTL, cot / MTL, x3, layout == 3, st);
-      case 2: return launch_large_q<2>(p, MTL, cot / MTL, x3, layout == 3, st);
-      case 3: return launch_large_q<3>(p, MTL, cot / MTL, x3, layout == 3, st);
-      default: return launch_large_q<4>(p, MTL, cot / MTL, x3, layout == 3, st);
+      case 1: return launch_large_q<1>(p, MTL, cot / MTL, x3, st);
+      case 2: return launch_large_q<2>(p, MTL, cot / MTL, x3, st);
+      case 3: return launch_large_q<3>(p, MTL, cot / MTL, x3, st);
+      default: return launch_large_q<4>(p, MTL, cot / MTL, x3, st);
     }
   }
-  B200_CHECK_ARG(layout == 0, "conv_gpl: a dense-first pair list (layout 1 / 3) only serves the large-input kernel "
+  B200_CHECK_ARG(layout == 0, "conv_gpl: a centre-first pair list (layout 1) only serves the large-input kernel "
                               "(ask b200scn_conv_gpl_layout first)");
   // small inputs: narrow passes unless the tiles alone already cover the SMs twice
   // (n_out_expect: how many rows the level really has when n_out_cap is only a buffer capacity)

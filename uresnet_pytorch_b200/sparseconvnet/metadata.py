@@ -225,7 +225,7 @@ class Metadata(object):
     # -- grouped pair lists (tensor-core convolution input) ------------------------------------
     def _build_gpl(self, lv, table, parent, kofs, K, size_key=None, layout=0):
         """Pair list over the rows of `lv` (the OUTPUT rows of the convolution that will use it).
-        layout: b200scn_gpl_build's (0 = offset-major, read by every kernel; 1 / 3 = dense-first, large-input
+        layout: b200scn_gpl_build's (0 = offset-major, read by every kernel; 1 = centre first, large-input
         convolution kernel only -- no per-offset index, so no weight gradient walks it)."""
         L = _lib.load()
         rows = lv.rows
@@ -265,7 +265,7 @@ class Metadata(object):
 
     def subm_gpl(self, spatial_size, filter_size, layout=0):
         """Pair list of the submanifold rules.  The layout-0 list carries `variant(layout)`, which hands out (and
-        builds on first use) the dense-first lists the large-input convolution kernel prefers."""
+        builds on first use) the centre-first list the large-input convolution kernel prefers."""
         self._note("subm_gpl", tuple(spatial_size), filter_size, layout)
         lv = self.level(spatial_size)
         key = ("subm", filter_size) if layout == 0 else ("subm", filter_size, layout)
