@@ -79,7 +79,7 @@ class Trainer(object):
         self.train = train
         self.events_per_step = max(int(events_per_step), 1)
         self.overlap_wgrad = overlap_wgrad
-        self.overlap_allreduce = overlap_allreduce
+        self.overlap_allreduce = overlap_allreduce and not os.environ.get("B200SCN_NO_OVERLAP_ALLREDUCE")  # (A/B runs)
         self.fused_loss = fused_loss  # head + loss + their backward in three kernels (csrc/headloss.cu)
         self.input_format = input_format
         self.math_mode = scn.config.math_mode if math_mode is None else math_mode
@@ -605,5 +605,10 @@ def init_distributed():
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        # The gradient all-reduce runs next to the outer level's backward kernels, which fill the SMs: with NCCL's
+        # default channel count its kernel gets few CTAs scheduled and outlives the backward pass.  Measured on 2
+        # GPUs (profiles/README.md section 0.1): 4.39 ms per step by default, 4.29 with NCCL_MIN_CTAS=32, 4.51 / 4.64
+        # with NCCL_MAX_CTAS=4 / 2.
+        os.environ.setdefault("NCCL_MIN_CTAS", "32")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     return rank, local, world
