@@ -192,6 +192,7 @@ struct GplParams {
   int warps, split;  // split != 0: the CTA's warps share one tile
   uint32_t ones;     // 0xffffffff (opaque to the compiler)
   uint32_t zero;     // 0 (opaque to the compiler)
+  int layout;        // pair-list layout (b200scn_gpl_build)
 };
 
 __device__ __forceinline__ float2 lds64(uint32_t a) {
@@ -330,7 +331,10 @@ __global__ void __launch_bounds__(kLargeWarps * 32, 1) k_conv_gpl(const GplParam
   for (int64_t wt = wt_begin; wt < wt_end; ++wt) {
     const int base = (int)(wt * R);
     __syncwarp();
-    for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // centre-first lists: every row of the tile is first WRITTEN by its centre group (C = 0), which precedes all
+    // other groups of the tile -- nothing to clear (the dummy row of the padding slots may hold anything)
+    if (p.layout != 1)
+      for (int e = lane; e < (R + 1) * C4; e += 32) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int gb = __ldg(p.tile_off + wt), ge = __ldg(p.tile_off + wt + 1);
     __syncwarp();
 
@@ -1005,7 +1009,7 @@ extern "C" int b200scn_conv_gpl(const float* in, int64_t ldi, const float* W, co
   p.tile_off = tile_off; p.tile_end = tile_end; p.g_rec = reinterpret_cast<const int4*>(g_rec); p.Q = Cin / 16;
   p.K = K; p.n_cap = n_out_cap; p.n_dev = n_out_dev; p.out = out; p.ldo = (int)ldo; p.accumulate = accumulate;
   p.res = res; p.ldr = (int)ldr;
-  p.warps = 8; p.split = 1; p.ones = 0xffffffffu; p.zero = 0u;
+  p.warps = 8; p.split = 1; p.ones = 0xffffffffu; p.zero = 0u; p.layout = layout;
 
   const int MTL = large_pass_width(tile_rows, tile_end == nullptr, n_out_cap, Cin, Cout, K, x3);
   B200_CHECK_ARG(layout != 3 || x3, "conv_gpl: layout-3 pair lists are served in the tf32x3 mode only");
