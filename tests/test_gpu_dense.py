@@ -43,6 +43,47 @@ def test_dense_model_matches_reference_golden(dim):
     assert (num / den) ** 0.5 <= 2e-3
 
 
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+def test_dense_model_uf16_tensor_core_modes_match_reference_golden(mode):
+    """uf = 16, two levels: every 3^3 / 2^3 layer but the 1 -> 16 stem and the 16 -> 5 head runs on the tcgen05
+    kernel (`k_dense_conv_tc`, Cin == 16 or Cin % 32 == 0) and the tensor-core weight gradient.  Golden vectors
+    from the UNMODIFIED reference model on torch-CPU (tests/golden/make_dense_golden.py::main_uf16): logits in
+    full, gradients as norm + three seeded projections per parameter tensor.  3xTF32 must be fp32-equivalent;
+    single-pass TF32 is the reduced-precision mode (10-bit mantissa operands)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_dense_golden import grad_probes
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.dense import DenseUResNet
+    g = np.load(os.path.join(GOLDEN, "dense_uf16_3d.npz"))
+    flags = small_flags(DATA_DIM=3, SPATIAL_SIZE=int(g["ss"]), URESNET_FILTERS=int(g["uf"]),
+                        URESNET_NUM_STRIDES=int(g["uns"]))
+    net = DenseUResNet(flags)
+    sd = {k[3:]: torch.from_numpy(g[k].astype(np.float32) if g[k].dtype == np.float16 else g[k])
+          for k in g.files if k.startswith("sd.")}
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    net.cuda().train()
+    out_tol, grad_tol = {"tf32x3": (2e-4, 2e-3), "tf32": (2e-2, 3e-2)}[mode]
+    with scn.math({"tf32x3": scn.MATH_TF32X3, "tf32": scn.MATH_TF32}[mode]):
+        out = net(torch.from_numpy(g["x"].astype(np.float32)).cuda())
+        (out * torch.from_numpy(g["w"].astype(np.float32)).cuda()).sum().backward()
+    ref = torch.from_numpy(g["out"])
+    err = (out.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    worst = 0.0
+    for name, p in net.named_parameters():
+        if "gnorm." + name not in g.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        a = p.grad.detach().cpu().double().numpy().ravel()
+        norm = float(g["gnorm." + name])
+        proj = grad_probes(name, a.size) @ a
+        d = max(abs(float(np.sqrt((a * a).sum())) - norm), float(np.abs(proj - g["gproj." + name]).max()) / 3.0)
+        worst = max(worst, d / max(norm, 1e-12))
+    print("dense uf16 %s: logits max|d| %.2e of scale, worst gradient tensor %.2e of its norm" % (mode, err, worst))
+    assert err <= out_tol and worst <= grad_tol, (err, worst)
+
+
 @pytest.mark.parametrize("dims,k,stride,cin,cout", [(3, 3, 1, 3, 5), (3, 3, 2, 4, 8), (3, 1, 2, 8, 4), (2, 3, 2, 5, 7),
                                                     (3, 3, 1, 16, 32)])
 def test_dense_conv_layer_against_torch(dims, k, stride, cin, cout):
