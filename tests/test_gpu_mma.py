@@ -152,6 +152,56 @@ def test_grouped_pair_lists_match_table(tile_rows, monkeypatch):
     assert off[-1] == len(rec)
 
 
+def test_centre_first_pair_list_matches_table(monkeypatch):
+    """Layout 1 (what the large-input kernel reads): the same (offset, in, out) triples as the neighbour table; every
+    tile starts with its 8 centre groups -- slot j of group s is output row 16 s + j, flag "C = 0" -- followed by the
+    other offsets in ascending order without flags."""
+    from uresnet_pytorch_b200 import sparseconvnet as scn
+    from uresnet_pytorch_b200.sparseconvnet.metadata import Metadata
+    from helpers import table_as_set
+    data, _ = event_blob(3, 48, dup=20, seed=12)
+    coords = torch.from_numpy(data[:, :4]).cuda()
+    monkeypatch.setattr(scn.config, "gpl_tile_rows", 128)
+    md = Metadata(3)
+    size = (48, 48, 48)
+    lv = md.set_input(coords, size)
+    gpl = md.subm_gpl(size, 3, 1)
+    assert gpl["layout"] == 1 and gpl["koff"] is None and gpl["tile_rows"] == 128
+    off = gpl["tile_off"].cpu().numpy()
+    rec = gpl["g_rec"].cpu().numpy().reshape(-1, 8, 4)
+    n, R, centre = lv.n, 128, 13
+    triples = set()
+    for tile in range(len(off) - 1):
+        assert off[tile + 1] - off[tile] >= R // 16
+        ks = []
+        for gi, grp in enumerate(range(off[tile], off[tile + 1])):
+            dense = gi < R // 16
+            for j in range(8):
+                word = int(rec[grp, j, 2]) & 0xFFFFFFFF
+                k, flags = (word >> 16) & 0xFF, word >> 24
+                assert rec[grp, j, 3] == 0 and flags == (1 if dense else 0)
+                assert (k == centre) == dense
+                for half in range(2):
+                    o = (word >> (8 * half)) & 0xFF
+                    if dense:
+                        assert o == 16 * gi + j + 8 * half                 # the slot IS the output row
+                        row = tile * R + o
+                        if row < n:
+                            assert rec[grp, j, half] == row                # centre rule: in == out
+                            triples.add((k, row, row))
+                        else:
+                            assert rec[grp, j, half] == 0                  # past the end: any valid input row
+                    elif o < R:
+                        triples.add((k, int(rec[grp, j, half]), tile * R + o))
+                    else:
+                        assert o == R and rec[grp, j, half] == 0
+            if not dense and j == 7:
+                ks.append(k)
+        assert ks == sorted(ks)
+    assert triples == table_as_set(md.subm_table(size, 3), n)
+    assert off[-1] == len(rec)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_gpl_and_pairs_kernels_agree(mode):
     """Same layer through the grouped-pair-list kernel and the in-kernel-listing kernel."""
