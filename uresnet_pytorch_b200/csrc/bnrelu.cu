@@ -50,7 +50,7 @@ Layout make_layout(int64_t n_cap, int C) {
   L.RL = C >= tpb ? 1 : tpb / C;
   L.threads = C * L.RL;
   int64_t b = cdiv(n_cap, rows_per_block_host(C));
-  const int64_t cap = (int64_t)sm_count() * 4;
+  const int64_t cap = (int64_t)sm_count() * 2;  // one co-resident wave of 1024-thread CTAs (see apply_grid)
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   L.blocks = (int)b;
