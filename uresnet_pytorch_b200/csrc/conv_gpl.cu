@@ -854,7 +854,7 @@ extern "C" int b200scn_gpl_tile_rows(int64_t n) {
   static int64_t t128 = -1, t64 = -1;  // B200SCN_GPL_T128 / B200SCN_GPL_T64 override the row thresholds (A/B runs)
   if (t128 < 0) {
     const char* e = getenv("B200SCN_GPL_T128");
-    t128 = e ? atoll(e) : 12288;
+    t128 = e ? atoll(e) : 60000;  // (12288 until round 2: c3 10.9 -> 10.1 ms, c2 4.18 -> 4.16 ms, c5 unchanged)
     e = getenv("B200SCN_GPL_T64");
     t64 = e ? atoll(e) : 5120;
   }
