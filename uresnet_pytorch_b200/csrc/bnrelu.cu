@@ -684,7 +684,7 @@ k_bn_bwd_fused(const float* __restrict__ x, int64_t ldx, const float* __restrict
 
 // Grid of the single-launch variants, or 0 when the input is too large for them (two-kernel path).
 // n_expect: rows a typical event holds at this level (0 = unknown: use the capacity).
-int fused_grid(int64_t n_cap, int64_t n_expect, int C, const Layout& L) {
+int fused_grid(int64_t n_cap, int64_t n_expect, int C, const Layout& L, bool bwd = false) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("B200SCN_BN_FUSED");
@@ -705,8 +705,15 @@ int fused_grid(int64_t n_cap, int64_t n_expect, int C, const Layout& L) {
     maxg = e ? atoi(e) : 64;  // measured: 64 CTAs beat 148 (profiles/README.md)
     if (maxg < 1 || maxg > sms) maxg = sms;
   }
+  static int maxg_bwd = 0;  // B200SCN_BN_FUSED_MAXG_BWD: CTA cap of the backward kernel alone (A/B runs)
+  if (maxg_bwd == 0) {
+    const char* e = getenv("B200SCN_BN_FUSED_MAXG_BWD");
+    maxg_bwd = e ? atoi(e) : 96;  // twice the data of the forward kernel (x and dy): c2 4.154 ms at 64, 4.134 at 32, 4.041 at 96, 4.048 at 128
+    if (maxg_bwd < 1 || maxg_bwd > sms) maxg_bwd = sms;
+  }
   int64_t g = cdiv(elems, (int64_t)L.threads * vpt);
-  if (g > maxg) g = maxg;
+  const int cap_g = bwd ? maxg_bwd : maxg;
+  if (g > cap_g) g = cap_g;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -845,7 +852,7 @@ extern "C" int b200scn_bn_bwd_sync(const float* x, int64_t ldx, const float* dy,
   B200_CHECK_ARG(C >= 1 && C <= 1024, "bn: C must be 1..1024 (got %d)", C);
   B200_CHECK_ARG(scratch_bytes >= b200scn_bn_scratch_bytes(n_cap, C), "bn_bwd: scratch too small");
   Layout L = make_layout(n_cap < 1 ? 1 : n_cap, C);
-  const int G = (sync != nullptr && n_cap > 0) ? fused_grid(n_cap, n_expect, C, L) : 0;
+  const int G = (sync != nullptr && n_cap > 0) ? fused_grid(n_cap, n_expect, C, L, true) : 0;
   if (G == 0)
     return b200scn_bn_bwd(x, ldx, dy, lddy, n_cap, n_dev, C, gamma, beta, mean, invstd, leak, train, dx, lddx, dgamma,
                           dbeta, scratch, scratch_bytes, stream);
