@@ -96,3 +96,39 @@ def test_bench_pool_is_size_bucketed_and_rank_specific():
     assert n0 == sorted(n0) and n1 == sorted(n1) and n0 != n1
     assert sorted(len(d) for d, _ in q0) == n0  # same events, different order
     assert all(d.shape[1] == 5 and l.shape == (len(d), 1) for d, l in p0)
+
+
+def test_bench_keeps_stdout_to_one_json_line():
+    """bench.py's contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 behind Python's
+    back (NCCL prints its version there when the first communicator is created -- it preceded the JSON line of the
+    2-GPU run): bench._own_stdout() points descriptor 1 at stderr and keeps the real stdout for Python's print."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; bench._own_stdout(); "
+            "os.write(1, b'NCCL version 0.0.0+banner\\n'); os.system('echo from-a-child-process'); "
+            "print(json.dumps({'ok': 1}))") % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().splitlines() == ['{"ok": 1}'], r.stdout
+    assert "banner" in r.stderr and "from-a-child-process" in r.stderr
+
+
+def test_bench_reference_arm_line_shape():
+    """`bench.py --impl reference`: one line, the GPU arm's metric / unit / config, impl = reference, cpu_baseline of
+    kind "port", e2e with zero copy bytes (the tier's reading of the bench contract)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200SCN_REF_BUDGET_S="5", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--config", "c1"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "voxels/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"] and d["value"] > 0
