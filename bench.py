@@ -14,6 +14,13 @@ stream with a 256 MB L2 flush between steps (outside the events); barrier +
 torch.cuda.synchronize() on both sides; MAX over ranks.  `value` = steps on inputs already
 resident in HBM; `e2e` = the same metric through Trainer.train_step(host blob) with the
 pinned H2D copy of the float64 blob and the D2H read of the loss inside the timed region.
+
+`roofline` (rank 0, before the process group exists): the level-0 SubmanifoldConvolution 16->16 forward over 128
+concatenated events (working set > L2), CUDA events on the launching stream, L2 flushed -- algorithmic bytes /
+launch time against the measured copy bandwidth; `roofline.rulebook` times the hash build, the neighbour table
+and the pair-list build of the same workload; `roofline.step_frac` relates the WHOLE step's compulsory bytes to
+`ms_per_step`.  `cpu_baseline` (N = 1 only): the reference arm in a clean child process.  stdout carries the one
+JSON line and nothing else (`_own_stdout`); at N > 1 the processes leave without tearing NCCL down.
 """
 import argparse
 import json
